@@ -1,0 +1,198 @@
+"""Generate tests/golden/*.npz by running the reference's own code (see ref_loader.py).
+
+Run in the build container only:  ``python tests/golden/make_golden.py``
+
+What comes from where
+---------------------
+* ``ref_*`` arrays are produced by the reference's method bodies executed verbatim:
+  ``_pairwise_potential``, ``_edge_weight_undirected_vec``, ``_connected_edge``,
+  ``_pairwise_compare``, ``_compute_posteriors_graph`` (+ ``_compute_cost_v1``,
+  ``_pairwise_compare_ensemble``/``_single``), ``_predict_posteriors`` (statistics
+  triple and the queue tuple), ``predict`` / ``_estimate_state_graphcuts_gco`` (the
+  arguments handed to ``pygco.cut_general_graph``), base.py's statistics helpers and
+  utility.py's edge-list builders.
+* ``logprob`` comes from the restated sklearn-0.18 density (the real one is not
+  installable here); it is an *input* to the reference code above, and is pinned
+  separately against scipy in tests/test_oracle_golden.py.
+* labels returned by the pygco stub are chosen by this script (arg-min of the unary with
+  a few seeded flips) -- GCO itself is exercised in tests/test_gco.py.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_loader  # noqa: E402
+from oracle import phmrf_oracle as orc  # noqa: E402
+
+
+class _Recorder:
+    """Stand-in for the ``pygco`` module: records the call, returns preset labels."""
+
+    def __init__(self):
+        self.calls = []
+        self.next_labels = None
+
+    def cut_general_graph(self, edges, edge_weights, unary_cost, pairwise_cost, n_iter=-1, algorithm='expansion',
+                          init_labels=None, down_weight_factor=None):
+        self.calls.append(dict(edges=np.array(edges), edge_weights=np.array(edge_weights),
+                               unary_cost=np.array(unary_cost), pairwise_cost=np.array(pairwise_cost),
+                               n_iter=n_iter, algorithm=algorithm, init_labels=np.array(init_labels),
+                               down_weight_factor=down_weight_factor))
+        return self.next_labels(unary_cost)
+
+
+class _Queue:
+    def __init__(self):
+        self.items = []
+
+    def put(self, x):
+        self.items.append(x)
+
+
+def synth_features(rng, N, d, zero_frac=0.3):
+    base = rng.gamma(2.0, 0.6, size=(N, 1))
+    z = base + 0.5 * rng.standard_normal((N, d))
+    X = np.log1p(np.maximum(z, 0.0))
+    X[rng.random((N, d)) < zero_frac * 0.5] = 0.0  # per-entry zeros
+    X[rng.random(N) < zero_frac * 0.3] = 0.0  # whole-node zeros (empty bins in every species)
+    return X
+
+
+def synth_model(rng, K, d):
+    means = rng.uniform(0.0, 2.0, size=(K, d))
+    covars = np.empty((K, d, d))
+    for k in range(K):
+        A = rng.standard_normal((d, d)) * 0.4
+        covars[k] = A @ A.T + (0.05 + 0.5 * rng.random()) * np.eye(d) + 1e-3 * np.eye(d)
+    return means, covars
+
+
+def region_geometry(util, rng, kind, n1, n2, d):
+    """Build (X, edge_list) for one region through the reference's own edge builders."""
+    if kind == "diag":
+        serial = np.asarray([i * n2 + j for i in range(n1) for j in range(i, n2)])
+        X = synth_features(rng, len(serial), d)
+        el = util["edge_weightlist_grid3_undirected_unsym"](X, serial, n2, '', 8)
+    else:
+        serial = np.asarray([i * n2 + j for i in range(n1) for j in range(n2)])
+        X = synth_features(rng, len(serial), d)
+        el = util["edge_weightlist_grid3_undirected"](X, serial, (n1, n2), '', 8)
+    return X, np.asarray(el, dtype=np.float64)
+
+
+def flatten_ragged(lists):
+    off = np.zeros(len(lists) + 1, dtype=np.int64)
+    for i, l in enumerate(lists):
+        off[i + 1] = off[i] + len(l)
+    flat = np.asarray([x for l in lists for x in l], dtype=np.int64)
+    return flat, off
+
+
+def make_case(name, seed, regions, d, K, beta, beta1, estimate_type, isolate=()):
+    rng = np.random.default_rng(seed)
+    util = ref_loader.load_utility(["mapping_Idx", "_sort_array", "edge_weightlist_grid3_undirected_unsym",
+                                    "edge_weightlist_grid3_undirected"])
+    rec = _Recorder()
+    cls = ref_loader.build_reference_class({
+        "pygco": rec,
+        "log_multivariate_normal_density":
+            lambda X, m, c, t: orc.log_multivariate_normal_density_full(X, m, c),
+    })
+
+    Xs, els, len_vec = [], [], []
+    s = 0
+    for r, (kind, n1, n2) in enumerate(regions):
+        X, el = region_geometry(util, rng, kind, n1, n2, d)
+        if r in dict(isolate):
+            node = dict(isolate)[r]
+            el = el[(el[:, 0] != node) & (el[:, 1] != node)]
+        Xs.append(X)
+        els.append(el)
+        len_vec.append([len(X), s, s + len(X), n1, n2, 0, 0, r, 1 if kind == "diag" else 0, 21])
+        s += len(X)
+    X_all = np.concatenate(Xs, axis=0)
+    means, covars = synth_model(rng, K, d)
+
+    m = object.__new__(cls)
+    m.n_components, m.n_features = K, d
+    m.beta, m.beta1, m.estimate_type = beta, beta1, estimate_type
+    m.covariance_type = 'full'
+    m.means_, m._covars_ = means, covars
+    m.len_vec = len_vec
+    m.edge_potential = m._pairwise_potential()
+    (m.edge_weightList_undirected_vec, m.edge_idList_undirected_vec,
+     m.neighbor_edgeIdx_vec) = m._edge_weight_undirected_vec(X_all, len_vec, els)
+    m.labels_local = rng.integers(0, K, size=len(X_all)).astype(np.int64)
+    m.labels = m.labels_local.copy()
+
+    flip_rng = np.random.default_rng(seed + 1)
+
+    def choose(unary):
+        lab = np.argmin(unary, axis=1)
+        flips = flip_rng.random(len(lab)) < 0.15
+        lab[flips] = flip_rng.integers(0, K, size=int(flips.sum()))
+        return lab.astype(np.int64)
+
+    rec.next_labels = choose
+
+    out = dict(d=d, K=K, beta=beta, beta1=beta1, estimate_type=estimate_type, n_regions=len(regions),
+               X=X_all, means=means, covars=covars, len_vec=np.asarray(len_vec, dtype=np.int64),
+               ref_V=m.edge_potential, init_labels=m.labels_local.copy())
+    q = _Queue()
+    stats_total = m._initialize_sufficient_statistics()
+    for r in range(len(regions)):
+        m._predict_posteriors(X_all, len_vec, r, q)
+        rid, stats, labels, c_pair, c_pair_norm, c_unary, c_total = q.items[-1]
+        call = rec.calls[-1]
+        s1, s2 = len_vec[r][1], len_vec[r][2]
+        logprob = -call["unary_cost"]
+        pp = m._pairwise_compare(labels, m.neighbor_edgeIdx_vec[r], m.edge_weightList_undirected_vec[r],
+                                 m.edge_idList_undirected_vec[r])
+        post = m._compute_posteriors_graph(X_all[s1:s2], labels, logprob, r)[0]
+        flat, off = flatten_ragged(m.neighbor_edgeIdx_vec[r])
+        p = "r%d_" % r
+        out.update({
+            p + "edge_list": els[r],
+            p + "ref_edge_w": m.edge_weightList_undirected_vec[r],
+            p + "ref_edge_ids": m.edge_idList_undirected_vec[r],
+            p + "ref_inc_flat": flat, p + "ref_inc_off": off,
+            p + "logprob": logprob,
+            p + "ref_gco_unary": call["unary_cost"], p + "ref_gco_V": call["pairwise_cost"],
+            p + "ref_gco_w": call["edge_weights"], p + "ref_gco_edges": call["edges"],
+            p + "ref_gco_init": call["init_labels"], p + "ref_gco_n_iter": call["n_iter"],
+            p + "ref_gco_algorithm": call["algorithm"],
+            p + "ref_gco_dwf_is_none": call["down_weight_factor"] is None,
+            p + "labels": np.asarray(labels, dtype=np.int64),
+            p + "ref_pp": pp, p + "ref_post": post,
+            p + "ref_costs": np.asarray([c_pair, c_pair_norm, c_unary, c_total]),
+            p + "ref_stats_post": stats["post"], p + "ref_stats_obs": stats["obs"],
+            p + "ref_stats_obsobsT": stats["obs*obs.T"],
+        })
+        stats_total = m._accumulate_sufficient_statistics_1(stats_total, stats)
+    out.update(ref_total_post=stats_total["post"], ref_total_obs=stats_total["obs"],
+               ref_total_obsobsT=stats_total["obs*obs.T"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "N =", len(X_all), "E =", [len(e) for e in els])
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference tree not present; fixtures can only be regenerated in the build container")
+    make_case("case_diag_w", 101, [("diag", 14, 14)], d=4, K=6, beta=1.0, beta1=0.1, estimate_type=3)
+    make_case("case_two_regions", 202, [("diag", 11, 11), ("rect", 7, 9)], d=5, K=8, beta=0.7, beta1=0.5,
+              estimate_type=3, isolate=((1, 17),))
+    make_case("case_unweighted_iso", 303, [("diag", 10, 10)], d=3, K=4, beta=2.0, beta1=0.1, estimate_type=0,
+              isolate=((0, 23),))
+    make_case("case_d9_k30", 404, [("diag", 16, 16)], d=9, K=30, beta=1.0, beta1=0.1, estimate_type=3)
+
+
+if __name__ == "__main__":
+    main()
