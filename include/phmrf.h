@@ -1,0 +1,160 @@
+/*
+ * phmrf.h -- C ABI of the B200-native Phylo-HMRF E-step hot path (libphmrf.so).
+ *
+ * The reference (ma-compbio/Phylo-HMRF) has no FFI of its own: its boundary is a set of
+ * Python methods plus two third-party callables.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every host buffer is owned by the caller and is not
+ *     referenced after the call returns; device memory lives behind the opaque handles.
+ *   - all entry points return 0 on success and a negative PHMRF_E_* code on failure and
+ *     never call exit()/throw across the ABI; phmrf_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - handles are not thread-safe; distinct regions may be driven from distinct threads.
+ *   - [N,K] host arrays are C-order (row = node), exactly as the reference's NumPy arrays.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     PHMRF_E_CUDA.
+ */
+#ifndef PHMRF_H_
+#define PHMRF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHMRF_ABI_VERSION 1
+
+enum {
+    PHMRF_OK = 0,
+    PHMRF_E_INVALID = -1,     /* bad argument (shape, null pointer, id out of range)            */
+    PHMRF_E_CUDA = -2,        /* CUDA runtime error / no device                                 */
+    PHMRF_E_NOT_SPD = -3,     /* covariance not symmetric positive-definite (reference raises
+                                 ValueError via sklearn 0.18 gmm.py / base.py:526-538)          */
+    PHMRF_E_STATE = -4,       /* call order violated (e.g. quantise before emit)                */
+    PHMRF_E_UNSUPPORTED = -5  /* shape outside the compiled kernel range                        */
+};
+
+typedef struct phmrf_ctx phmrf_ctx;       /* one model (K states, d leaves) on one device        */
+typedef struct phmrf_region phmrf_region; /* one synteny region, or one row band of a region     */
+
+int phmrf_abi_version(void);
+const char *phmrf_last_error(void);
+
+/* ------------------------------------------------------------------ model ------------- */
+
+/* Replaces the state the hot path reads from the model object: means_ [K,d], _covars_
+ * [K,d,d] (phylo_hmrf.py:1521-1524) and edge_potential [K,K] (phylo_hmrf.py:99,524-536). */
+int phmrf_ctx_create(int device, int n_states, int n_features, phmrf_ctx **out);
+int phmrf_ctx_destroy(phmrf_ctx *ctx);
+
+/* Host side of sklearn-0.18 _log_multivariate_normal_density_full (behind
+ * phylo_hmrf.py:266-268): per-state lower Cholesky (retry with +1e-7*I, else
+ * PHMRF_E_NOT_SPD), log-det, and the inverse factor the kernels consume.  V is the label
+ * compatibility matrix handed to pygco (phylo_hmrf.py:495); the Potts form beta*(1-I)
+ * produced by _pairwise_potential takes the fast path, any other V the general one. */
+int phmrf_set_model(phmrf_ctx *ctx, const double *means, const double *covars, const double *V);
+
+/* ------------------------------------------------------------------ region ------------ */
+
+/* Replaces the per-region inputs of _predict_posteriors (phylo_hmrf.py:297-322): X[s1:s2]
+ * and the output of _edge_weight_undirected_vec / _connected_edge (phylo_hmrf.py:567-598,
+ * 674-689): edge_ids [E,2] (int64, id1<id2, sorted by (id1,id2)) and edge weights
+ * w = exp(-beta1*d_ij) [E].
+ *
+ * Row-band sharding: a band owns nodes [own_offset, own_offset+n_own) of a label window of
+ * n_window nodes; edge ids are window-local and every edge incident to an owned node must
+ * be present (edges between two non-owned nodes are ignored).  A whole region is the
+ * special case own_offset=0, n_own=n_window.  X holds the n_own owned rows.
+ * stream: a cudaStream_t to enqueue on (e.g. torch.cuda.Stream.cuda_stream) or NULL for a
+ * stream owned by the region. */
+int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t n_window, int64_t own_offset,
+                        const int64_t *edge_ids, const double *edge_w, int64_t n_edges, void *stream,
+                        phmrf_region **out);
+/* Re-upload the owned rows of X [n_own,d] into a resident region (the `X[s1:s2]` argument
+ * of _predict_posteriors, phylo_hmrf.py:297-303, when the caller passes it every
+ * iteration).  Enqueued on the region's stream; X must stay valid until the next sync. */
+int phmrf_region_update_X(phmrf_region *r, const double *X);
+int phmrf_region_destroy(phmrf_region *r);
+int phmrf_region_sync(phmrf_region *r);
+int64_t phmrf_region_device_bytes(const phmrf_region *r);
+
+/* ------------------------------------------------------------------ phase A ----------- */
+
+/* _compute_log_likelihood (phylo_hmrf.py:266-268, called at :489): enqueue the emission
+ * kernel; the [K,N] log-likelihood stays on the device.  absmax_out (nullable) receives
+ * max|logp| over the owned nodes (the data term of pygco's down_weight_factor); asking for
+ * it synchronises the region's stream. */
+int phmrf_emit_loglik(phmrf_region *r, double *absmax_out);
+
+/* Copy the log-likelihood to a host [n_own,K] array (return value of
+ * _compute_log_likelihood / second return of _estimate_state_graphcuts_gco). */
+int phmrf_get_logprob(phmrf_region *r, double *logprob_out);
+
+/* Replace the resident log-likelihood by a caller-supplied [n_own,K] array: the `logprob`
+ * argument of _compute_posteriors_graph / _compute_cost_v1 (phylo_hmrf.py:334, 374) when
+ * it is not the array the emission kernel just produced. */
+int phmrf_set_logprob(phmrf_region *r, const double *logprob);
+
+/* The float->int conversion inside pygco.cut_general_graph (yujiali/pygco, called at
+ * phylo_hmrf.py:496-498 with down_weight_factor=None):
+ *   dwf = max(max|unary|, max|w|*max(V)) + 1e-10
+ *   unary_i32 = trunc((-logp/dwf)*1e5); w_i32 = trunc((w/dwf)*1e3); V_i32 = trunc(V*1e3)
+ * dwf_in > 0 overrides the region-local value (bands of one region must share the
+ * all-reduced maximum).  Any output pointer may be NULL (the integer unary then stays on
+ * the device for phmrf_labels_argmin_unary).  Entries whose scaled value lies within
+ * relative `tol` of a truncation boundary are reported: flat indices (node*K+state) go to
+ * boundary_idx (capacity boundary_cap), their total count to n_boundary. */
+int phmrf_quantise(phmrf_region *r, double dwf_in, double tol, int32_t *unary_i32_out, int32_t *w_i32_out,
+                   int32_t *V_i32_out, double *dwf_out, int64_t *boundary_idx, int64_t boundary_cap,
+                   int64_t *n_boundary);
+
+/* ------------------------------------------------------------------ phase B ----------- */
+
+/* Labels of the whole window (owned nodes + halo), as returned by the graph cut
+ * (phylo_hmrf.py:496-498) -- int32, values in [0,K). */
+int phmrf_set_labels(phmrf_region *r, const int32_t *labels_window);
+
+/* Bench / test stand-in for the graph cut: labels = arg-min_k of the device
+ * integer unary (first minimum).  Only valid for whole regions (n_own == n_window). */
+int phmrf_labels_argmin_unary(phmrf_region *r, int32_t *labels_out);
+
+/* _compute_posteriors_graph + _compute_cost_v1 + the statistics triple
+ * (phylo_hmrf.py:334-355, 374-468, 311-314) in one fused pass over the owned nodes:
+ *   stats_out [K*(1+d+d*d)] = post[K] | obs[K,d] | obs*obs.T[K,d,d]
+ *   cost_sums_out [3] = sum_i sum_{e in inc(i)} V[l_nbr,l_i]*w_e ; sum_i ln(pwn[i,l_i]+1e-16) ;
+ *                       sum_i logp[i,l_i]          (un-normalised, so that bands add up)
+ * post_out (nullable) receives the posteriors [n_own,K].  estimate_type==3 weights the
+ * pairwise term by w (phylo_hmrf.py:431-434, 460-462).  The results also stay in a device
+ * buffer of K*(1+d+d*d)+3 doubles (phmrf_stats_device_ptr) for an NCCL all-reduce. */
+int phmrf_estep_stats(phmrf_region *r, int estimate_type, double *post_out, double *stats_out,
+                      double *cost_sums_out);
+/* _pairwise_compare (phylo_hmrf.py:398-410): the neighbour-weighted pairwise potential
+ * pp [n_own,K] for the current labels.  The fused E-step never materialises it; this entry
+ * point exists for signature parity and for tests. */
+int phmrf_pairwise_potential(phmrf_region *r, int estimate_type, double *pp_out);
+void *phmrf_stats_device_ptr(phmrf_region *r);
+int64_t phmrf_stats_len(const phmrf_ctx *ctx);
+
+/* Enqueue-only forms used by the bench (no host copies, no synchronisation). */
+int phmrf_emit_loglik_async(phmrf_region *r);
+int phmrf_quantise_async(phmrf_region *r, double dwf_in, double tol);
+int phmrf_estep_stats_async(phmrf_region *r, int estimate_type);
+
+/* Number of kernel launches this library has enqueued so far (bench "gpu_launches"). */
+int64_t phmrf_launch_count(void);
+
+/* ------------------------------------------------------------------ probes ------------ */
+
+/* FP64 FMA-pipe peak of the current device, measured with a dependent-chain DFMA
+ * micro-benchmark (the roofline denominator BASELINE.md asks the builder to measure). */
+int phmrf_probe_fp64_tflops(int device, double *tflops_out);
+/* which: see csrc/probe.cu; returns a throughput figure in Gop/s for pipe exploration. */
+int phmrf_probe(int device, int which, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHMRF_H_ */

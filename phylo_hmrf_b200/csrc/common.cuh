@@ -1,0 +1,82 @@
+// Shared declarations between the host API (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/phmrf.h"
+
+namespace phmrf {
+
+constexpr int kMinFeatures = 1;
+constexpr int kMaxFeatures = 12;      // D is a template parameter of the kernels
+constexpr int kModelConstDoubles = 7680;  // 60 KB of the 64 KB constant bank
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+void count_launch(int n = 1);
+
+#define PHMRF_CUDA(expr)                                                       \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return ::phmrf::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// Per-state emission parameters as the kernels consume them (built on the host from the
+// Cholesky factor): z = Wh*x - ch with Wh = sqrt(1/2)*L^-1 (lower triangular, packed by
+// rows), ch = Wh*mu, and logp = -(hc + sum z^2) with hc = (d*ln(2pi) + logdet)/2.
+__host__ __device__ constexpr int model_stride(int D) { return D * (D + 1) / 2 + D + 1; }
+__host__ __device__ constexpr int n_stat_features(int D) { return 1 + D + D * (D + 1) / 2; }
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- phase A (kernels_a.cu) -----------------------------------------------------------
+// Upload the packed model into the constant bank of the current device.
+int upload_model_constant(const double *packed, int n_doubles, cudaStream_t s);
+// X_aos [n,D] row-major -> X_soa [D][ld]
+int launch_aos_to_soa(const double *X_aos, double *X_soa, int64_t n, int D, int64_t ld, cudaStream_t s);
+// [n,K] row-major -> [K][ld]
+int launch_aos_to_soa_k(const double *aos, double *soa, int64_t n, int K, int64_t ld, cudaStream_t s);
+// logp [K][ld] -> out [n,K] row-major (also used for posteriors)
+int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t ld, cudaStream_t s);
+// emission: logp[k][i] for i<n, block maxima of |logp| folded into *absmax_bits (uint64 bit
+// pattern of a non-negative double, atomicMax).
+int launch_emit(const double *X_soa, int64_t n, int64_t ld, int D, int K, const double *model_global,
+                bool model_in_const, double *logp, unsigned long long *absmax_bits, int sm_count,
+                cudaStream_t s);
+// dwf = max(absmax_u, wmax*vmax) + 1e-10 unless dwf_in > 0; written to *dwf_dev.
+int launch_dwf(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in, double *dwf_dev,
+               cudaStream_t s);
+// unary_i32[i*K+k] = trunc(((-logp[k][i])/dwf)*1e5); boundary entries appended to blist.
+int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, const double *dwf_dev, double tol,
+                          int32_t *unary, long long *blist, long long bcap, unsigned long long *bcount,
+                          int sm_count, cudaStream_t s);
+// w_i32[e] = trunc((w[e]/dwf)*1e3)
+int launch_quantise_edges(const double *w, int64_t E, const double *dwf_dev, int32_t *w_i32, cudaStream_t s);
+int launch_argmin_unary(const int32_t *unary, int64_t n, int K, int32_t *labels, cudaStream_t s);
+
+// ---- phase B (kernels_b.cu) -----------------------------------------------------------
+struct EstepArgs {
+    const double *X_soa;      // [D][ld]
+    const double *logp;       // [K][ld]
+    const int32_t *labels;    // [n_window]
+    const int32_t *nbr_id;    // [W][ld] window-local neighbour id, -1 = none
+    const double *nbr_w;      // [W][ld] edge weight per slot
+    const double *V;          // [K][K] (general path only)
+    double beta;              // Potts strength (fast path)
+    int potts;
+    int64_t n, ld, own_offset;
+    int D, K, W, estimate_type;
+    double *post_soa;         // nullable [K][ld]
+    double *pp_soa;           // nullable [K][ld] pairwise potential (signature-parity output)
+    double *partials;         // [grid][K*F + 4] per-block partial sums
+    double *stats_out;        // [K*(1+D+D*D) + 3]
+};
+// Returns the grid size it will use (for sizing `partials`) when args == nullptr.
+int estep_grid(int D, int K, int sm_count);
+int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s);
+
+// ---- probes (probe.cu) ----------------------------------------------------------------
+int run_probe(int which, double *out);
+
+}  // namespace phmrf

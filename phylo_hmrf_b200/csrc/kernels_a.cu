@@ -1,0 +1,338 @@
+// Phase A of the Phylo-HMRF E-step on sm_100a: emission log-likelihood, the deterministic
+// max|logp| reduction behind pygco's down_weight_factor, and the integer cost arrays.
+//
+// Reference arithmetic: sklearn-0.18 _log_multivariate_normal_density_full behind
+// phylo_hmrf.py:266-268; unary = -logprob (phylo_hmrf.py:490); pygco's float->int
+// conversion behind phylo_hmrf.py:496-498.
+#include "common.cuh"
+
+namespace phmrf {
+
+__constant__ double c_model[kModelConstDoubles];
+
+int upload_model_constant(const double *packed, int n_doubles, cudaStream_t s) {
+    if (n_doubles > kModelConstDoubles) {
+        set_error("model does not fit the constant bank");
+        return PHMRF_E_UNSUPPORTED;
+    }
+    PHMRF_CUDA(cudaMemcpyToSymbolAsync(c_model, packed, sizeof(double) * n_doubles, 0, cudaMemcpyHostToDevice, s));
+    return PHMRF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// layout helpers (one-off per region / per host read-back; not on the per-iteration path)
+// ------------------------------------------------------------------------------------
+__global__ void aos_to_soa_kernel(const double *__restrict__ aos, double *__restrict__ soa, int64_t n, int D,
+                                  int64_t ld) {
+    int64_t total = n * D;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e / D;
+        int j = (int)(e - i * D);
+        soa[j * ld + i] = aos[e];
+    }
+}
+
+int launch_aos_to_soa(const double *X_aos, double *X_soa, int64_t n, int D, int64_t ld, cudaStream_t s) {
+    if (n == 0) return PHMRF_OK;
+    int64_t total = n * D;
+    int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    aos_to_soa_kernel<<<grid, 256, 0, s>>>(X_aos, X_soa, n, D, ld);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+int launch_aos_to_soa_k(const double *aos, double *soa, int64_t n, int K, int64_t ld, cudaStream_t s) {
+    return launch_aos_to_soa(aos, soa, n, K, ld, s);
+}
+
+// [K][ld] -> [n][K] through a 32x32 shared-memory tile so both sides stay coalesced.
+__global__ void soa_to_aos_kernel(const double *__restrict__ soa, double *__restrict__ aos, int64_t n, int K,
+                                  int64_t ld) {
+    __shared__ double tile[32][33];
+    int64_t n_tiles_i = (n + 31) / 32;
+    int k_tiles = (K + 31) / 32;
+    int64_t total = n_tiles_i * k_tiles;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        int64_t ti = t / k_tiles;
+        int tk = (int)(t - ti * k_tiles);
+        int64_t i0 = ti * 32;
+        int k0 = tk * 32;
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int k = k0 + r;
+            int64_t i = i0 + threadIdx.x;
+            tile[r][threadIdx.x] = (k < K && i < n) ? soa[k * ld + i] : 0.0;
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int64_t i = i0 + r;
+            int k = k0 + threadIdx.x;
+            if (i < n && k < K) aos[i * K + k] = tile[threadIdx.x][r];
+        }
+        __syncthreads();
+    }
+}
+
+int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t ld, cudaStream_t s) {
+    if (n == 0) return PHMRF_OK;
+    int64_t total = ((n + 31) / 32) * ((K + 31) / 32);
+    int grid = (int)(total < 148 * 8 ? total : 148 * 8);
+    soa_to_aos_kernel<<<grid, dim3(32, 8), 0, s>>>(soa, aos, n, K, ld);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// A1: emission.  One thread owns NPT consecutive nodes; their d features sit in registers
+// and every state's packed factor is read through the constant bank (warp-uniform address),
+// so the inner loop is d(d+3)/2 DFMA per node-state and nothing else on the FP64 pipe.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long abs_bits(double v) {
+    return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+}
+
+template <int D, bool CONST_MODEL>
+__global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs, int64_t n, int64_t ld, int K,
+                                                    const double *__restrict__ model, double *__restrict__ logp,
+                                                    unsigned long long *absmax_bits) {
+    constexpr int PS = model_stride(D);
+    constexpr int NPT = 2;
+    unsigned long long amax = 0ull;
+    const int64_t n_pairs = ld / NPT;  // ld is a multiple of 64; the pad region holds zeros
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = p * NPT;
+        if (i0 >= n) break;
+        double x0[D], x1[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double2 v = *reinterpret_cast<const double2 *>(Xs + j * ld + i0);
+            x0[j] = v.x;
+            x1[j] = v.y;
+        }
+        const bool second = (i0 + 1 < n);
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            const double *m = CONST_MODEL ? (c_model + k * PS) : (model + (int64_t)k * PS);
+            double a0 = m[PS - 1], a1 = a0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const double ci = -m[D * (D + 1) / 2 + i];
+                double z0 = ci, z1 = ci;
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    const double w = m[i * (i + 1) / 2 + j];
+                    z0 = fma(w, x0[j], z0);
+                    z1 = fma(w, x1[j], z1);
+                }
+                a0 = fma(z0, z0, a0);
+                a1 = fma(z1, z1, a1);
+            }
+            const double l0 = -a0, l1 = -a1;
+            *reinterpret_cast<double2 *>(logp + k * ld + i0) = make_double2(l0, l1);
+            unsigned long long b0 = abs_bits(l0), b1 = second ? abs_bits(l1) : 0ull;
+            amax = b0 > amax ? b0 : amax;
+            amax = b1 > amax ? b1 : amax;
+        }
+    }
+    // warp -> block -> device maximum; integer max of the |.| bit pattern is order
+    // independent (deterministic) and lets a NaN win, like numpy's max.
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, amax, o);
+        amax = other > amax ? other : amax;
+    }
+    __shared__ unsigned long long wmax[8];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = wmax[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = wmax[w] > m ? wmax[w] : m;
+        atomicMax(absmax_bits, m);
+    }
+}
+
+template <int D>
+static int launch_emit_d(const double *Xs, int64_t n, int64_t ld, int K, const double *model, bool in_const,
+                         double *logp, unsigned long long *absmax_bits, int sm_count, cudaStream_t s) {
+    int64_t n_pairs = (n + 1) / 2;
+    int64_t blocks = (n_pairs + 255) / 256;
+    int64_t cap = (int64_t)sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    if (grid < 1) grid = 1;
+    if (in_const)
+        emit_kernel<D, true><<<grid, 256, 0, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
+    else
+        emit_kernel<D, false><<<grid, 256, 0, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+int launch_emit(const double *Xs, int64_t n, int64_t ld, int D, int K, const double *model_global,
+                bool model_in_const, double *logp, unsigned long long *absmax_bits, int sm_count,
+                cudaStream_t s) {
+    PHMRF_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(unsigned long long), s));
+    if (n == 0) return PHMRF_OK;
+    switch (D) {
+#define PHMRF_CASE(DD) \
+    case DD:           \
+        return launch_emit_d<DD>(Xs, n, ld, K, model_global, model_in_const, logp, absmax_bits, sm_count, s);
+        PHMRF_CASE(1) PHMRF_CASE(2) PHMRF_CASE(3) PHMRF_CASE(4) PHMRF_CASE(5) PHMRF_CASE(6)
+        PHMRF_CASE(7) PHMRF_CASE(8) PHMRF_CASE(9) PHMRF_CASE(10) PHMRF_CASE(11) PHMRF_CASE(12)
+#undef PHMRF_CASE
+    }
+    set_error("n_features outside [1,12]");
+    return PHMRF_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------
+// dwf = max(max|unary|, max|w| * max V) + 1e-10   (pygco, down_weight_factor=None)
+// ------------------------------------------------------------------------------------
+__global__ void dwf_kernel(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in,
+                           double *dwf_dev) {
+    if (dwf_in > 0.0) {
+        dwf_dev[0] = dwf_in;
+    } else {
+        double umax = __longlong_as_double((long long)absmax_bits[0]);
+        double pw = __dmul_rn(wmax, vmax);
+        // python's max(a, b) returns a unless b > a (so a NaN in `a` survives)
+        double m = (pw > umax) ? pw : umax;
+        dwf_dev[0] = __dadd_rn(m, 1e-10);
+    }
+    dwf_dev[1] = __longlong_as_double((long long)absmax_bits[0]);
+}
+
+int launch_dwf(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in, double *dwf_dev,
+               cudaStream_t s) {
+    dwf_kernel<<<1, 1, 0, s>>>(absmax_bits, wmax, vmax, dwf_in, dwf_dev);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// A2: integer unary.  Two separately rounded FP64 operations then truncation toward zero,
+// exactly numpy's ((u / dwf) * 1e5).astype(intc).  The [K][ld] -> [n][K] transposition goes
+// through shared memory so that both the FP64 reads and the int32 writes are coalesced.
+// ------------------------------------------------------------------------------------
+template <int TN>
+__global__ void __launch_bounds__(256) quantise_unary_kernel(const double *__restrict__ logp, int64_t n, int64_t ld,
+                                                              int K, const double *__restrict__ dwf_dev, double tol,
+                                                              int32_t *__restrict__ unary,
+                                                              long long *__restrict__ blist, long long bcap,
+                                                              unsigned long long *bcount) {
+    extern __shared__ int32_t tile[];  // [TN][K]
+    const double dwf = dwf_dev[0];
+    const int lane_n = threadIdx.x % TN;
+    const int kgrp = threadIdx.x / TN;
+    constexpr int KG = 256 / TN;
+    const int64_t n_tiles = (n + TN - 1) / TN;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t base = t * TN;
+        const int64_t i = base + lane_n;
+        const int cnt = (int)((n - base) < TN ? (n - base) : TN);
+        if (i < n) {
+            for (int k = kgrp; k < K; k += KG) {
+                const double u = -logp[k * ld + i];
+                const double tq = __dmul_rn(__ddiv_rn(u, dwf), 100000.0);
+                const int q = __double2int_rz(tq);
+                tile[lane_n * K + k] = q;
+                const double dist = fabs(tq - rint(tq));
+                if (dist <= tol * fmax(1.0, fabs(tq))) {
+                    unsigned long long pos = atomicAdd(bcount, 1ull);
+                    if ((long long)pos < bcap) blist[pos] = (long long)(i * K + k);
+                }
+            }
+        }
+        __syncthreads();
+        int32_t *dst = unary + base * K;
+        const int total = cnt * K;
+        if ((total & 3) == 0) {
+            const int4 *src4 = reinterpret_cast<const int4 *>(tile);
+            int4 *dst4 = reinterpret_cast<int4 *>(dst);
+            for (int e = threadIdx.x; e < (total >> 2); e += 256) dst4[e] = src4[e];
+        } else {
+            for (int e = threadIdx.x; e < total; e += 256) dst[e] = tile[e];
+        }
+        __syncthreads();
+    }
+}
+
+int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, const double *dwf_dev, double tol,
+                          int32_t *unary, long long *blist, long long bcap, unsigned long long *bcount,
+                          int sm_count, cudaStream_t s) {
+    PHMRF_CUDA(cudaMemsetAsync(bcount, 0, sizeof(unsigned long long), s));
+    if (n == 0) return PHMRF_OK;
+    const size_t budget = 200 * 1024;
+    int tn = 128;
+    while (tn > 32 && (size_t)tn * K * 4 > 48 * 1024) tn >>= 1;
+    size_t smem = (size_t)tn * K * 4;
+    if (smem > budget) {
+        set_error("n_states too large for the quantise tile");
+        return PHMRF_E_UNSUPPORTED;
+    }
+    int64_t n_tiles = (n + tn - 1) / tn;
+    int64_t cap = (int64_t)sm_count * 8;
+    int grid = (int)(n_tiles < cap ? n_tiles : cap);
+#define PHMRF_Q(TN)                                                                                          \
+    {                                                                                                        \
+        if (smem > 48 * 1024)                                                                                \
+            PHMRF_CUDA(cudaFuncSetAttribute(quantise_unary_kernel<TN>,                                       \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        quantise_unary_kernel<TN><<<grid, 256, smem, s>>>(logp, n, ld, K, dwf_dev, tol, unary, blist, bcap, \
+                                                          bcount);                                           \
+    }
+    if (tn == 128) PHMRF_Q(128) else if (tn == 64) PHMRF_Q(64) else PHMRF_Q(32)
+#undef PHMRF_Q
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+__global__ void quantise_edges_kernel(const double *__restrict__ w, int64_t E, const double *__restrict__ dwf_dev,
+                                      int32_t *__restrict__ out) {
+    const double dwf = dwf_dev[0];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = __double2int_rz(__dmul_rn(__ddiv_rn(w[e], dwf), 1000.0));
+}
+
+int launch_quantise_edges(const double *w, int64_t E, const double *dwf_dev, int32_t *w_i32, cudaStream_t s) {
+    if (E == 0) return PHMRF_OK;
+    int64_t blocks = (E + 255) / 256;
+    int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    quantise_edges_kernel<<<grid, 256, 0, s>>>(w, E, dwf_dev, w_i32);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+// Stand-in for the graph cut in benches/tests: first arg-min of the integer unary.
+__global__ void argmin_unary_kernel(const int32_t *__restrict__ unary, int64_t n, int K, int32_t *__restrict__ labels) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t *row = unary + i * K;
+        int best = 0;
+        int32_t bv = row[0];
+        for (int k = 1; k < K; ++k) {
+            int32_t v = row[k];
+            if (v < bv) {
+                bv = v;
+                best = k;
+            }
+        }
+        labels[i] = best;
+    }
+}
+
+int launch_argmin_unary(const int32_t *unary, int64_t n, int K, int32_t *labels, cudaStream_t s) {
+    if (n == 0) return PHMRF_OK;
+    int64_t blocks = (n + 255) / 256;
+    int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    argmin_unary_kernel<<<grid, 256, 0, s>>>(unary, n, K, labels);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+}  // namespace phmrf

@@ -1,0 +1,443 @@
+// Phase B of the Phylo-HMRF E-step on sm_100a: neighbour-weighted pairwise potential,
+// posteriors, the cost scalars and the M-step sufficient statistics in ONE pass over the
+// nodes (pp, the posteriors and the per-node features are never materialised in HBM).
+//
+// Reference arithmetic: _pairwise_compare/_pairwise_compareLocal (phylo_hmrf.py:398-436),
+// _compute_posteriors_graph (:334-355), _compute_cost_v1 (:374-396),
+// _pairwise_compare_ensemble/_single (:438-468), statistics triple (:311-314).
+//
+// Structure.  A warp owns 32 consecutive nodes per step (lane = node) and runs two phases:
+//   node phase  lane-private: gather neighbour labels, scatter beta*w into a shared-memory
+//               row (one row per node), stabilised soft-max over the K states, cost terms,
+//               and the per-node feature row y = (1, x, x (x) x packed) / normaliser.
+//   stat phase  S[k][f] += sum_n e[n][k] * y[n][f] is a (K x 32) x (32 x F) product whose
+//               K*F accumulators are spread over the lanes of the warp as TK x TF register
+//               tiles; rows are read back from shared memory as broadcast LDS.128.
+// Accumulators live in registers for the whole kernel; block partials are reduced in a
+// fixed order (deterministic) and a final kernel folds them and unpacks the symmetric
+// scatter into the reference's [K], [K,d], [K,d,d] layout.
+#include "common.cuh"
+
+namespace phmrf {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ constexpr int even_up(int v) { return (v + 1) & ~1; }
+// row strides (in doubles) are even (16-byte alignment of every row) with stride/2 odd, so
+// that the 128-bit column stores of the node phase are bank-conflict free.
+__host__ __device__ constexpr int pad_row(int v) { return (even_up(v) / 2) % 2 == 1 ? even_up(v) : even_up(v) + 2; }
+
+template <int D, int TK, int TF>
+struct Cfg {
+    static constexpr int F = n_stat_features(D);
+    static constexpr int TKs = even_up(TK);
+    static constexpr int TFs = even_up(TF);
+    static constexpr int NFT = (F + TF - 1) / TF;
+    static constexpr int RSY = pad_row(NFT * TFs);
+};
+
+// packed feature f -> value, everything resolved at compile time under full unrolling
+template <int D>
+__device__ __forceinline__ double feature_value(int f, const double (&x)[D], const double (&xs)[D], double inv) {
+    if (f == 0) return inv;
+    if (f <= D) return xs[f - 1];
+    int r = f - 1 - D;
+    int i = 0;
+    while (r >= D - i) {
+        r -= D - i;
+        ++i;
+    }
+    return xs[i] * x[i + r];
+}
+
+template <int D, int TK, int TF>
+__global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt_total, int kt_begin, int nkt_pass,
+                                                             int rsp, int first_pass) {
+    using C = Cfg<D, TK, TF>;
+    constexpr int F = C::F, TKs = C::TKs, TFs = C::TFs, NFT = C::NFT, RSY = C::RSY;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    double *Ps = smem + (size_t)warp * 32 * (rsp + RSY);
+    double *Ys = Ps + 32 * rsp;
+    double *Prow = Ps + lane * rsp;
+    double *Yrow = Ys + lane * RSY;
+
+    // lane -> (node subset, k tile, f tile) for the stat phase
+    const int tiles = nkt_pass * NFT;
+    const int NS = 32 / tiles;
+    const int sub = lane / tiles;
+    const int tl = lane - sub * tiles;
+    const int ktl = tl / NFT, ft = tl - ktl * NFT;
+    const bool lane_active = sub < NS && (kt_begin + ktl) < nkt_total;
+    const int kt = lane_active ? kt_begin + ktl : kt_begin;
+
+    double acc[TK][TF];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+        for (int j = 0; j < TF; ++j) acc[i][j] = 0.0;
+    double c_pair = 0.0, c_pwn = 0.0, c_un = 0.0;
+
+    const int K = a.K, W = a.W;
+    const int64_t n = a.n, ld = a.ld;
+    const int64_t n_tiles = (n + 31) >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * wpb + warp;
+    const int64_t warp_stride = (int64_t)gridDim.x * wpb;
+    const bool weighted = a.estimate_type == 3;
+
+    for (int64_t t = warp_global; t < n_tiles; t += warp_stride) {
+        const int64_t i_raw = (t << 5) + lane;
+        const bool valid = i_raw < n;
+        const int64_t i = valid ? i_raw : n - 1;
+        const int li = a.labels[a.own_offset + i];
+
+        // ---------------- node phase ----------------
+        double pmin = 0.0;  // min_k pp_k (stabilises the pairwise soft-max)
+        double pc = 0.0;
+        double wtot = 0.0;
+        if (a.potts) {
+            for (int c = 0; c < rsp; c += 2) *reinterpret_cast<double2 *>(Prow + c) = make_double2(0.0, 0.0);
+            double smax = 0.0;
+            int deg = 0;
+            for (int s = 0; s < W; ++s) {
+                const int j = a.nbr_id[s * ld + i];
+                if (j >= 0) {
+                    const int lj = a.labels[j];
+                    const double bw = weighted ? a.beta * a.nbr_w[s * ld + i] : a.beta;
+                    const int pos = (lj / TK) * TKs + (lj % TK);
+                    const double v = Prow[pos] + bw;
+                    Prow[pos] = v;
+                    smax = fmax(smax, v);
+                    wtot += bw;
+                    pc += (lj != li) ? bw : 0.0;
+                    ++deg;
+                }
+            }
+            if (deg == 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
+                wtot = a.beta;
+                Prow[(li / TK) * TKs + (li % TK)] = a.beta;
+                smax = a.beta;
+            }
+            // some state is absent among the neighbours unless one label carries every slot
+            pmin = wtot - smax;
+        } else {
+            int deg = 0;
+            for (int s = 0; s < W; ++s) deg += a.nbr_id[s * ld + i] >= 0;
+            pmin = INFINITY;
+            for (int k = 0; k < K; ++k) {
+                double pp = 0.0;
+                if (deg == 0) {
+                    pp = a.V[li * K + k];
+                } else {
+                    for (int s = 0; s < W; ++s) {
+                        const int j = a.nbr_id[s * ld + i];
+                        if (j >= 0) {
+                            const double ws = weighted ? a.nbr_w[s * ld + i] : 1.0;
+                            pp += a.V[a.labels[j] * K + k] * ws;
+                        }
+                    }
+                }
+                Prow[(k / TK) * TKs + (k % TK)] = pp;
+                pmin = fmin(pmin, pp);
+            }
+            for (int s = 0; s < W; ++s) {
+                const int j = a.nbr_id[s * ld + i];
+                if (j >= 0) pc += a.V[a.labels[j] * K + li] * (weighted ? a.nbr_w[s * ld + i] : 1.0);
+            }
+        }
+
+        // pass 1: a_k = logp_k - pp_k, its maximum, and the pairwise soft-max normaliser
+        double amax = -INFINITY, qsum = 0.0, a_li = 0.0, pp_li = 0.0;
+        const double q0 = exp(pmin - wtot);  // Potts: exp(-(pp - pmin)) of a state no neighbour carries
+        for (int ktile = 0; ktile < nkt_total; ++ktile) {
+#pragma unroll
+            for (int ii = 0; ii < TK; ++ii) {
+                const int k = ktile * TK + ii;
+                if (k < K) {
+                    const int pos = ktile * TKs + ii;
+                    const double sv = Prow[pos];
+                    double pp, q;
+                    if (a.potts) {
+                        pp = wtot - sv;
+                        const bool touched = sv != 0.0;
+                        q = q0;
+                        if (__any_sync(0xffffffffu, touched)) q = touched ? exp(pmin - pp) : q0;
+                    } else {
+                        pp = sv;
+                        q = exp(pmin - pp);
+                    }
+                    qsum += q;
+                    if (a.pp_soa != nullptr && first_pass && valid) a.pp_soa[k * ld + i] = pp;
+                    const double lp = a.logp[k * ld + i];
+                    const double ak = lp - pp;
+                    if (k == li) {
+                        a_li = lp;
+                        pp_li = pp;
+                    }
+                    Prow[pos] = ak;
+                    amax = fmax(amax, ak);
+                } else {
+                    if (ii < TKs) Prow[ktile * TKs + ii] = -INFINITY;
+                }
+            }
+            if (TK < TKs) Prow[ktile * TKs + TK] = -INFINITY;
+        }
+        // pass 2: e_k = exp(a_k - amax), normaliser
+        double esum = 0.0;
+        for (int c = 0; c < nkt_total * TKs; c += 2) {
+            double2 v = *reinterpret_cast<double2 *>(Prow + c);
+            v.x = exp(v.x - amax);
+            v.y = exp(v.y - amax);
+            esum += v.x + v.y;
+            *reinterpret_cast<double2 *>(Prow + c) = v;
+        }
+        const double inv = valid ? 1.0 / esum : 0.0;
+        if (first_pass && valid) {
+            c_pair += pc;
+            c_un += a_li;
+            c_pwn += log(exp(pmin - pp_li) / qsum + 1e-16);
+            if (a.post_soa != nullptr) {
+                for (int ktile = 0; ktile < nkt_total; ++ktile)
+#pragma unroll
+                    for (int ii = 0; ii < TK; ++ii) {
+                        const int k = ktile * TK + ii;
+                        if (k < K) a.post_soa[k * ld + i] = Prow[ktile * TKs + ii] * inv;
+                    }
+            }
+        }
+        {
+            double x[D], xs[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                x[j] = a.X_soa[j * ld + i];
+                xs[j] = x[j] * inv;
+            }
+#pragma unroll
+            for (int c = 0; c < RSY; c += 2) {
+                double2 v = make_double2(0.0, 0.0);
+                {
+                    const int tile0 = c / TFs, off0 = c % TFs;
+                    const int f0 = tile0 * TF + off0;
+                    if (tile0 < NFT && off0 < TF && f0 < F) v.x = feature_value<D>(f0, x, xs, inv);
+                    const int tile1 = (c + 1) / TFs, off1 = (c + 1) % TFs;
+                    const int f1 = tile1 * TF + off1;
+                    if (tile1 < NFT && off1 < TF && f1 < F) v.y = feature_value<D>(f1, x, xs, inv);
+                }
+                *reinterpret_cast<double2 *>(Yrow + c) = v;
+            }
+        }
+        __syncwarp();
+
+        // ---------------- stat phase ----------------
+        if (lane_active) {
+            const double *pb = Ps + kt * TKs;
+            const double *yb = Ys + ft * TFs;
+#pragma unroll 2
+            for (int nn = sub; nn < 32; nn += NS) {
+                double p[TKs], y[TFs];
+#pragma unroll
+                for (int c = 0; c < TKs; c += 2) {
+                    double2 v = *reinterpret_cast<const double2 *>(pb + nn * rsp + c);
+                    p[c] = v.x;
+                    p[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < TFs; c += 2) {
+                    double2 v = *reinterpret_cast<const double2 *>(yb + nn * RSY + c);
+                    y[c] = v.x;
+                    y[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < TF; ++jj) acc[ii][jj] = fma(p[ii], y[jj], acc[ii][jj]);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- block reduction (fixed order => deterministic) ----------------
+    __syncthreads();
+    double *red = smem;  // K*F + 3 doubles
+    const int KF = K * F;
+    if (kt_begin == 0 || true) {
+        for (int e = threadIdx.x; e < KF + 3; e += blockDim.x) red[e] = 0.0;
+    }
+    __syncthreads();
+    const int ns_total = 32 / tiles;
+    for (int w = 0; w < wpb; ++w) {
+        for (int s = 0; s < ns_total; ++s) {
+            if (warp == w && sub == s && lane_active) {
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii) {
+                    const int k = kt * TK + ii;
+#pragma unroll
+                    for (int jj = 0; jj < TF; ++jj) {
+                        const int f = ft * TF + jj;
+                        if (k < K && f < F) red[k * F + f] += acc[ii][jj];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // cost partial sums: warp shuffle tree, then warps in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_pair += __shfl_xor_sync(0xffffffffu, c_pair, o);
+        c_pwn += __shfl_xor_sync(0xffffffffu, c_pwn, o);
+        c_un += __shfl_xor_sync(0xffffffffu, c_un, o);
+    }
+    for (int w = 0; w < wpb; ++w) {
+        if (warp == w && lane == 0) {
+            red[KF + 0] += c_pair;
+            red[KF + 1] += c_pwn;
+            red[KF + 2] += c_un;
+        }
+        __syncthreads();
+    }
+    double *out = a.partials + (size_t)blockIdx.x * (KF + 3);
+    const int k_lo = kt_begin * TK, k_hi = min(K, (kt_begin + nkt_pass) * TK);
+    for (int e = threadIdx.x; e < KF + 3; e += blockDim.x) {
+        if (e >= KF) {
+            if (first_pass) out[e] = red[e];
+        } else {
+            const int k = e / F;
+            if (k >= k_lo && k < k_hi) out[e] = red[e];
+        }
+    }
+}
+
+// Fold the per-block partials (fixed order) and unpack to post[K] | obs[K,d] | obs*obs.T[K,d,d] | 3 cost sums.
+__global__ void estep_finalize_kernel(const double *__restrict__ partials, int n_blocks, int K, int D,
+                                      double *__restrict__ stats_out) {
+    const int F = n_stat_features(D);
+    const int KF = K * F;
+    const int n_out = K * (1 + D + D * D) + 3;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += gridDim.x * blockDim.x) {
+        int src;
+        if (o < K) {
+            src = o * F;
+        } else if (o < K + K * D) {
+            const int k = (o - K) / D, i = (o - K) % D;
+            src = k * F + 1 + i;
+        } else if (o < K + K * D + K * D * D) {
+            const int r = o - K - K * D;
+            const int k = r / (D * D), ij = r % (D * D);
+            int i = ij / D, j = ij % D;
+            if (i > j) {
+                const int tmp = i;
+                i = j;
+                j = tmp;
+            }
+            src = k * F + 1 + D + (i * D - i * (i - 1) / 2 + (j - i));
+        } else {
+            src = KF + (o - (K + K * D + K * D * D));
+        }
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * (KF + 3) + src];
+        stats_out[o] = s;
+    }
+}
+
+struct TileChoice {
+    int tk, tf;
+};
+
+// One (TK,TF) register tile per feature count; TF*NFT >= F with little waste, TK*TF <= 60.
+constexpr TileChoice tile_for(int D) {
+    switch (D) {
+        case 1: return {8, 3};
+        case 2: return {8, 6};
+        case 3: return {5, 10};
+        case 4: return {6, 8};
+        case 5: return {5, 11};
+        case 6: return {4, 14};
+        case 7: return {5, 12};
+        case 8: return {4, 15};
+        case 9: return {5, 11};
+        case 10: return {5, 11};
+        case 11: return {4, 13};
+        default: return {4, 13};
+    }
+}
+
+struct Plan {
+    int nkt_total, nkt_pass, n_pass, rsp, wpb, grid;
+    size_t smem;
+};
+
+template <int D>
+Plan make_plan(int K, int sm_count, int64_t n) {
+    constexpr TileChoice tc = tile_for(D);
+    using C = Cfg<D, tc.tk, tc.tf>;
+    Plan p;
+    p.nkt_total = (K + tc.tk - 1) / tc.tk;
+    int max_kt = 32 / C::NFT;
+    p.nkt_pass = p.nkt_total < max_kt ? p.nkt_total : max_kt;
+    p.n_pass = (p.nkt_total + p.nkt_pass - 1) / p.nkt_pass;
+    p.rsp = pad_row(p.nkt_total * C::TKs);
+    size_t per_warp = (size_t)32 * (p.rsp + C::RSY) * sizeof(double);
+    size_t budget = 220 * 1024;
+    int wpb = (int)(budget / per_warp);
+    if (wpb > 8) wpb = 8;
+    p.wpb = wpb;
+    size_t red_bytes = ((size_t)K * C::F + 3) * sizeof(double);
+    p.smem = per_warp * (wpb > 0 ? wpb : 1);
+    if (p.smem < red_bytes) p.smem = red_bytes;
+    int64_t n_tiles = (n + 31) / 32;
+    int64_t want = wpb > 0 ? (n_tiles + wpb - 1) / wpb : 1;
+    p.grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    return p;
+}
+
+template <int D>
+int launch_estep_d(const EstepArgs &a, int sm_count, cudaStream_t s) {
+    constexpr TileChoice tc = tile_for(D);
+    Plan p = make_plan<D>(a.K, sm_count, a.n);
+    if (p.wpb < 1 || p.smem > 227 * 1024) {
+        set_error("n_states too large for the E-step shared-memory rows");
+        return PHMRF_E_UNSUPPORTED;
+    }
+    auto kern = estep_kernel<D, tc.tk, tc.tf>;
+    PHMRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    for (int pass = 0; pass < p.n_pass; ++pass) {
+        kern<<<p.grid, p.wpb * 32, p.smem, s>>>(a, p.nkt_total, pass * p.nkt_pass, p.nkt_pass, p.rsp, pass == 0);
+        count_launch();
+        PHMRF_CUDA(cudaGetLastError());
+    }
+    estep_finalize_kernel<<<8, 256, 0, s>>>(a.partials, p.grid, a.K, D, a.stats_out);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+}  // namespace
+
+int estep_grid(int D, int K, int sm_count) {
+    (void)D;
+    (void)K;
+    return sm_count;
+}
+
+int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s) {
+    if (a.n == 0) {
+        PHMRF_CUDA(cudaMemsetAsync(a.stats_out, 0, sizeof(double) * (a.K * (1 + a.D + a.D * a.D) + 3), s));
+        return PHMRF_OK;
+    }
+    switch (a.D) {
+#define PHMRF_CASE(DD) \
+    case DD:           \
+        return launch_estep_d<DD>(a, sm_count, s);
+        PHMRF_CASE(1) PHMRF_CASE(2) PHMRF_CASE(3) PHMRF_CASE(4) PHMRF_CASE(5) PHMRF_CASE(6)
+        PHMRF_CASE(7) PHMRF_CASE(8) PHMRF_CASE(9) PHMRF_CASE(10) PHMRF_CASE(11) PHMRF_CASE(12)
+#undef PHMRF_CASE
+    }
+    set_error("n_features outside [1,12]");
+    return PHMRF_E_UNSUPPORTED;
+}
+
+}  // namespace phmrf
