@@ -34,6 +34,7 @@ WORKLOADS = {
     "cfg3_chr1_50kb": (4979, 5, 20, 1),
     "cfg4_genome_50kb_band": (4979, 5, 20, 1),
     "tiny": (400, 9, 30, 1),
+    "mid_d9_k30": (5000, 9, 30, 1),
 }
 METRIC = "node-states/sec per EM iteration (emission+costs+stats)"
 UNIT = "node-states/s"

@@ -24,11 +24,6 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return PHMRF_E_CUDA;
 }
 
-// Which ctx's model currently occupies the constant bank of each device.
-static std::mutex g_const_mutex;
-static const void *g_const_owner[64] = {nullptr};
-static unsigned long long g_const_version[64] = {0};
-
 }  // namespace phmrf
 
 using namespace phmrf;
@@ -41,9 +36,8 @@ struct phmrf_ctx {
     unsigned long long version = 0;
     std::vector<double> packed;  // K * model_stride(D)
     std::vector<double> V;       // K*K
-    double *d_model = nullptr;   // global copy (fallback when the constant bank is too small)
+    double *d_model = nullptr;   // K * model_stride(D) packed factors
     double *d_V = nullptr;
-    bool use_const = true;
 };
 
 struct phmrf_region {
@@ -119,22 +113,6 @@ int ensure_scratch(phmrf_region *r, int64_t elems) {
     return rc;
 }
 
-int ensure_model_on_device(phmrf_region *r) {
-    phmrf_ctx *ctx = r->ctx;
-    if (!ctx->use_const) return PHMRF_OK;
-    std::lock_guard<std::mutex> lock(g_const_mutex);
-    const int dev = ctx->device;
-    if (g_const_owner[dev] == ctx && g_const_version[dev] == ctx->version) return PHMRF_OK;
-    // another model (or none) occupies the bank: drain the device, then replace it
-    PHMRF_CUDA(cudaDeviceSynchronize());
-    int rc = upload_model_constant(ctx->packed.data(), (int)ctx->packed.size(), r->stream);
-    if (rc != PHMRF_OK) return rc;
-    PHMRF_CUDA(cudaStreamSynchronize(r->stream));
-    g_const_owner[dev] = ctx;
-    g_const_version[dev] = ctx->version;
-    return PHMRF_OK;
-}
-
 }  // namespace
 
 extern "C" {
@@ -165,7 +143,6 @@ int phmrf_ctx_create(int device, int n_states, int n_features, phmrf_ctx **out) 
         return cuda_fail(cudaGetLastError(), "cudaDeviceGetAttribute", __FILE__, __LINE__);
     }
     const size_t md = (size_t)n_states * model_stride(n_features);
-    ctx->use_const = md <= (size_t)kModelConstDoubles;
     if (cudaMalloc((void **)&ctx->d_model, sizeof(double) * md) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_V, sizeof(double) * n_states * n_states) != cudaSuccess) {
         cudaError_t err = cudaGetLastError();
@@ -180,10 +157,6 @@ int phmrf_ctx_create(int device, int n_states, int n_features, phmrf_ctx **out) 
 int phmrf_ctx_destroy(phmrf_ctx *ctx) {
     if (!ctx) return PHMRF_OK;
     cudaSetDevice(ctx->device);
-    {
-        std::lock_guard<std::mutex> lock(g_const_mutex);
-        if (g_const_owner[ctx->device] == ctx) g_const_owner[ctx->device] = nullptr;
-    }
     cudaFree(ctx->d_model);
     cudaFree(ctx->d_V);
     delete ctx;
@@ -229,16 +202,14 @@ int phmrf_set_model(phmrf_ctx *ctx, const double *means, const double *covars, c
         }
         double *p = packed.data() + (size_t)k * PS;
         const double *mu = means + (size_t)k * D;
+        p[0] = half_log_2pi_d + 0.5 * logdet;
+        int q = 1;
         for (int i = 0; i < D; ++i) {
             double ci = 0.0;
-            for (int j = 0; j <= i; ++j) {
-                const double w = rs2 * Wm[i * D + j];
-                p[i * (i + 1) / 2 + j] = w;
-                ci += w * mu[j];
-            }
-            p[D * (D + 1) / 2 + i] = ci;
+            for (int j = 0; j <= i; ++j) ci += rs2 * Wm[i * D + j] * mu[j];
+            p[q++] = ci;
+            for (int j = 0; j <= i; ++j) p[q++] = rs2 * Wm[i * D + j];
         }
-        p[PS - 1] = half_log_2pi_d + 0.5 * logdet;
     }
     // label compatibility: Potts beta*(1-I) (phylo_hmrf.py:524-536) takes the fast path
     bool potts = true;
@@ -449,9 +420,8 @@ int phmrf_emit_loglik_async(phmrf_region *r) {
     }
     int rc = set_device(ctx);
     if (rc) return rc;
-    if ((rc = ensure_model_on_device(r)) != PHMRF_OK) return rc;
-    rc = launch_emit(r->d_X, r->n, r->ld, ctx->D, ctx->K, ctx->d_model, ctx->use_const, r->d_logp, r->d_absmax,
-                     ctx->sm_count, r->stream);
+    rc = launch_emit(r->d_X, r->n, r->ld, ctx->D, ctx->K, ctx->d_model, r->d_logp, r->d_absmax, ctx->sm_count,
+                     r->stream);
     if (rc == PHMRF_OK) {
         r->have_logp = true;
         r->have_unary = false;

@@ -10,7 +10,6 @@ namespace phmrf {
 
 constexpr int kMinFeatures = 1;
 constexpr int kMaxFeatures = 12;      // D is a template parameter of the kernels
-constexpr int kModelConstDoubles = 7680;  // 60 KB of the 64 KB constant bank
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -23,16 +22,15 @@ void count_launch(int n = 1);
     } while (0)
 
 // Per-state emission parameters as the kernels consume them (built on the host from the
-// Cholesky factor): z = Wh*x - ch with Wh = sqrt(1/2)*L^-1 (lower triangular, packed by
-// rows), ch = Wh*mu, and logp = -(hc + sum z^2) with hc = (d*ln(2pi) + logdet)/2.
+// Cholesky factor): z = Wh*x - ch with Wh = sqrt(1/2)*L^-1 (lower triangular), ch = Wh*mu,
+// and logp = -(hc + sum z^2) with hc = (d*ln(2pi) + logdet)/2.  Stored as the stream the
+// emission kernel consumes: hc, then for each row i: ch_i, Wh_i0 .. Wh_ii.
 __host__ __device__ constexpr int model_stride(int D) { return D * (D + 1) / 2 + D + 1; }
 __host__ __device__ constexpr int n_stat_features(int D) { return 1 + D + D * (D + 1) / 2; }
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- phase A (kernels_a.cu) -----------------------------------------------------------
-// Upload the packed model into the constant bank of the current device.
-int upload_model_constant(const double *packed, int n_doubles, cudaStream_t s);
 // X_aos [n,D] row-major -> X_soa [D][ld]
 int launch_aos_to_soa(const double *X_aos, double *X_soa, int64_t n, int D, int64_t ld, cudaStream_t s);
 // [n,K] row-major -> [K][ld]
@@ -42,8 +40,7 @@ int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t 
 // emission: logp[k][i] for i<n, block maxima of |logp| folded into *absmax_bits (uint64 bit
 // pattern of a non-negative double, atomicMax).
 int launch_emit(const double *X_soa, int64_t n, int64_t ld, int D, int K, const double *model_global,
-                bool model_in_const, double *logp, unsigned long long *absmax_bits, int sm_count,
-                cudaStream_t s);
+                double *logp, unsigned long long *absmax_bits, int sm_count, cudaStream_t s);
 // dwf = max(absmax_u, wmax*vmax) + 1e-10 unless dwf_in > 0; written to *dwf_dev.
 int launch_dwf(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in, double *dwf_dev,
                cudaStream_t s);

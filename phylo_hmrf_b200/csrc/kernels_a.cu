@@ -8,17 +8,6 @@
 
 namespace phmrf {
 
-__constant__ double c_model[kModelConstDoubles];
-
-int upload_model_constant(const double *packed, int n_doubles, cudaStream_t s) {
-    if (n_doubles > kModelConstDoubles) {
-        set_error("model does not fit the constant bank");
-        return PHMRF_E_UNSUPPORTED;
-    }
-    PHMRF_CUDA(cudaMemcpyToSymbolAsync(c_model, packed, sizeof(double) * n_doubles, 0, cudaMemcpyHostToDevice, s));
-    return PHMRF_OK;
-}
-
 // ------------------------------------------------------------------------------------
 // layout helpers (one-off per region / per host read-back; not on the per-iteration path)
 // ------------------------------------------------------------------------------------
@@ -84,56 +73,93 @@ int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t 
 }
 
 // ------------------------------------------------------------------------------------
-// A1: emission.  One thread owns NPT consecutive nodes; their d features sit in registers
-// and every state's packed factor is read through the constant bank (warp-uniform address),
-// so the inner loop is d(d+3)/2 DFMA per node-state and nothing else on the FP64 pipe.
+// A1: emission.  One thread owns NPT consecutive nodes whose d features sit in registers.
+// The packed per-state factors (a stream in the order the arithmetic consumes it:
+// hc, then per row i: c_i, W_i0..W_ii) are staged once per block in shared memory and read
+// back as warp-uniform (broadcast) 128-bit loads, so the inner loop is d(d+3)/2 DFMA per
+// node-state and NPT*d(d+3)/2 DFMA per (PS+1)/2 shared loads.  (A first version indexed
+// the constant bank with the state id: ncu showed the ADU pipe at 81 % and the FP64 pipe
+// at 20 % -- indexed LDC is the wrong tool for per-state tables.)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long abs_bits(double v) {
     return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
 }
 
-template <int D, bool CONST_MODEL>
+template <int D, bool SMEM_MODEL>
 __global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs, int64_t n, int64_t ld, int K,
                                                     const double *__restrict__ model, double *__restrict__ logp,
                                                     unsigned long long *absmax_bits) {
     constexpr int PS = model_stride(D);
-    constexpr int NPT = 2;
+    constexpr int PSs = (PS + 1) & ~1;  // even stride: every state starts 16-byte aligned
+    constexpr int NPT = 4;
+    extern __shared__ __align__(16) double smodel[];
+    if (SMEM_MODEL) {
+        for (int e = threadIdx.x; e < K * PSs; e += blockDim.x) {
+            const int k = e / PSs, q = e - k * PSs;
+            smodel[e] = q < PS ? model[(int64_t)k * PS + q] : 0.0;
+        }
+        __syncthreads();
+    }
     unsigned long long amax = 0ull;
-    const int64_t n_pairs = ld / NPT;  // ld is a multiple of 64; the pad region holds zeros
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs;
+    const int64_t n_groups = ld / NPT;  // ld is a multiple of 64; the pad region holds zeros
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_groups;
          p += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i0 = p * NPT;
         if (i0 >= n) break;
-        double x0[D], x1[D];
+        double x[NPT][D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            double2 v = *reinterpret_cast<const double2 *>(Xs + j * ld + i0);
-            x0[j] = v.x;
-            x1[j] = v.y;
+            const double2 v0 = *reinterpret_cast<const double2 *>(Xs + j * ld + i0);
+            const double2 v1 = *reinterpret_cast<const double2 *>(Xs + j * ld + i0 + 2);
+            x[0][j] = v0.x;
+            x[1][j] = v0.y;
+            x[2][j] = v1.x;
+            x[3][j] = v1.y;
         }
-        const bool second = (i0 + 1 < n);
-#pragma unroll 2
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
-            const double *m = CONST_MODEL ? (c_model + k * PS) : (model + (int64_t)k * PS);
-            double a0 = m[PS - 1], a1 = a0;
+            double mv[PSs];
+            if (SMEM_MODEL) {
+                const double2 *m2 = reinterpret_cast<const double2 *>(smodel + k * PSs);
+#pragma unroll
+                for (int c = 0; c < PSs / 2; ++c) {
+                    const double2 v = m2[c];
+                    mv[2 * c] = v.x;
+                    mv[2 * c + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < PS; ++c) mv[c] = __ldg(model + (int64_t)k * PS + c);
+            }
+            double acc[NPT];
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) acc[u] = mv[0];
+            int q = 1;
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                const double ci = -m[D * (D + 1) / 2 + i];
-                double z0 = ci, z1 = ci;
+                double z[NPT];
+#pragma unroll
+                for (int u = 0; u < NPT; ++u) z[u] = -mv[q];
+                ++q;
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
-                    const double w = m[i * (i + 1) / 2 + j];
-                    z0 = fma(w, x0[j], z0);
-                    z1 = fma(w, x1[j], z1);
+#pragma unroll
+                    for (int u = 0; u < NPT; ++u) z[u] = fma(mv[q], x[u][j], z[u]);
+                    ++q;
                 }
-                a0 = fma(z0, z0, a0);
-                a1 = fma(z1, z1, a1);
+#pragma unroll
+                for (int u = 0; u < NPT; ++u) acc[u] = fma(z[u], z[u], acc[u]);
             }
-            const double l0 = -a0, l1 = -a1;
-            *reinterpret_cast<double2 *>(logp + k * ld + i0) = make_double2(l0, l1);
-            unsigned long long b0 = abs_bits(l0), b1 = second ? abs_bits(l1) : 0ull;
-            amax = b0 > amax ? b0 : amax;
-            amax = b1 > amax ? b1 : amax;
+            double l[NPT];
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) l[u] = -acc[u];
+            *reinterpret_cast<double2 *>(logp + k * ld + i0) = make_double2(l[0], l[1]);
+            *reinterpret_cast<double2 *>(logp + k * ld + i0 + 2) = make_double2(l[2], l[3]);
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) {
+                const unsigned long long b = (i0 + u < n) ? abs_bits(l[u]) : 0ull;
+                amax = b > amax ? b : amax;
+            }
         }
     }
     // warp -> block -> device maximum; integer max of the |.| bit pattern is order
@@ -154,31 +180,35 @@ __global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs
 }
 
 template <int D>
-static int launch_emit_d(const double *Xs, int64_t n, int64_t ld, int K, const double *model, bool in_const,
-                         double *logp, unsigned long long *absmax_bits, int sm_count, cudaStream_t s) {
-    int64_t n_pairs = (n + 1) / 2;
-    int64_t blocks = (n_pairs + 255) / 256;
-    int64_t cap = (int64_t)sm_count * 8;
+static int launch_emit_d(const double *Xs, int64_t n, int64_t ld, int K, const double *model, double *logp,
+                         unsigned long long *absmax_bits, int sm_count, cudaStream_t s) {
+    constexpr int PSs = (model_stride(D) + 1) & ~1;
+    const int64_t n_groups = (n + 3) / 4;
+    const int64_t blocks = (n_groups + 255) / 256;
+    const int64_t cap = (int64_t)sm_count * 4;
     int grid = (int)(blocks < cap ? blocks : cap);
     if (grid < 1) grid = 1;
-    if (in_const)
-        emit_kernel<D, true><<<grid, 256, 0, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
-    else
+    const size_t smem = (size_t)K * PSs * sizeof(double);
+    if (smem <= 160 * 1024) {
+        if (smem > 48 * 1024)
+            PHMRF_CUDA(cudaFuncSetAttribute(emit_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_kernel<D, true><<<grid, 256, smem, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
+    } else {
         emit_kernel<D, false><<<grid, 256, 0, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
+    }
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     return PHMRF_OK;
 }
 
-int launch_emit(const double *Xs, int64_t n, int64_t ld, int D, int K, const double *model_global,
-                bool model_in_const, double *logp, unsigned long long *absmax_bits, int sm_count,
-                cudaStream_t s) {
+int launch_emit(const double *Xs, int64_t n, int64_t ld, int D, int K, const double *model_global, double *logp,
+                unsigned long long *absmax_bits, int sm_count, cudaStream_t s) {
     PHMRF_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(unsigned long long), s));
     if (n == 0) return PHMRF_OK;
     switch (D) {
 #define PHMRF_CASE(DD) \
     case DD:           \
-        return launch_emit_d<DD>(Xs, n, ld, K, model_global, model_in_const, logp, absmax_bits, sm_count, s);
+        return launch_emit_d<DD>(Xs, n, ld, K, model_global, logp, absmax_bits, sm_count, s);
         PHMRF_CASE(1) PHMRF_CASE(2) PHMRF_CASE(3) PHMRF_CASE(4) PHMRF_CASE(5) PHMRF_CASE(6)
         PHMRF_CASE(7) PHMRF_CASE(8) PHMRF_CASE(9) PHMRF_CASE(10) PHMRF_CASE(11) PHMRF_CASE(12)
 #undef PHMRF_CASE

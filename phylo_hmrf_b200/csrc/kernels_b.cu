@@ -8,14 +8,17 @@
 //
 // Structure.  A warp owns 32 consecutive nodes per step (lane = node) and runs two phases:
 //   node phase  lane-private: gather neighbour labels, scatter beta*w into a shared-memory
-//               row (one row per node), stabilised soft-max over the K states, cost terms,
-//               and the per-node feature row y = (1, x, x (x) x packed) / normaliser.
+//               row (one row per node), soft-max over the K states, cost terms, and the
+//               per-node feature row y = (1, x, x (x) x packed) / normaliser.
 //   stat phase  S[k][f] += sum_n e[n][k] * y[n][f] is a (K x 32) x (32 x F) product whose
 //               K*F accumulators are spread over the lanes of the warp as TK x TF register
 //               tiles; rows are read back from shared memory as broadcast LDS.128.
 // Accumulators live in registers for the whole kernel; block partials are reduced in a
 // fixed order (deterministic) and a final kernel folds them and unpacks the symmetric
 // scatter into the reference's [K], [K,d], [K,d,d] layout.
+#include <cfloat>
+#include <utility>
+
 #include "common.cuh"
 
 namespace phmrf {
@@ -26,7 +29,7 @@ constexpr int kThreads = 256;
 
 __host__ __device__ constexpr int even_up(int v) { return (v + 1) & ~1; }
 // row strides (in doubles) are even (16-byte alignment of every row) with stride/2 odd, so
-// that the 128-bit column stores of the node phase are bank-conflict free.
+// that the 128-bit column accesses of the node phase are bank-conflict free.
 __host__ __device__ constexpr int pad_row(int v) { return (even_up(v) / 2) % 2 == 1 ? even_up(v) : even_up(v) + 2; }
 
 template <int D, int TK, int TF>
@@ -38,19 +41,53 @@ struct Cfg {
     static constexpr int RSY = pad_row(NFT * TFs);
 };
 
-// packed feature f -> value, everything resolved at compile time under full unrolling
-template <int D>
-__device__ __forceinline__ double feature_value(int f, const double (&x)[D], const double (&xs)[D], double inv) {
-    if (f == 0) return inv;
-    if (f <= D) return xs[f - 1];
-    int r = f - 1 - D;
+// ---- per-node feature row, resolved at compile time ------------------------------------
+__host__ __device__ constexpr int tri_row_of(int r, int D) {
     int i = 0;
     while (r >= D - i) {
         r -= D - i;
         ++i;
     }
-    return xs[i] * x[i + r];
+    return i;
 }
+__host__ __device__ constexpr int tri_col_of(int r, int D) {
+    int i = 0;
+    while (r >= D - i) {
+        r -= D - i;
+        ++i;
+    }
+    return i + r;
+}
+
+// value stored at position POS of the Y row: feature f = tile*TF + off, or 0 on padding.
+template <int D, int TF, int POS>
+__device__ __forceinline__ double y_at(const double (&x)[D], const double (&xs)[D], double inv) {
+    constexpr int TFs = even_up(TF);
+    constexpr int F = n_stat_features(D);
+    constexpr int NFT = (F + TF - 1) / TF;
+    constexpr int tile = POS / TFs, off = POS % TFs;
+    constexpr int f = tile * TF + off;
+    if constexpr (tile >= NFT || off >= TF || f >= F) {
+        return 0.0;
+    } else if constexpr (f == 0) {
+        return inv;
+    } else if constexpr (f <= D) {
+        return xs[f - 1];
+    } else {
+        constexpr int r = f - 1 - D;
+        return xs[tri_row_of(r, D)] * x[tri_col_of(r, D)];
+    }
+}
+
+template <int D, int TF, int... Cs>
+__device__ __forceinline__ void write_y_row(double *Yrow, const double (&x)[D], const double (&xs)[D], double inv,
+                                            std::integer_sequence<int, Cs...>) {
+    ((*reinterpret_cast<double2 *>(Yrow + 2 * Cs) =
+          make_double2(y_at<D, TF, 2 * Cs>(x, xs, inv), y_at<D, TF, 2 * Cs + 1>(x, xs, inv))),
+     ...);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int D, int TK, int TF>
 __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt_total, int kt_begin, int nkt_pass,
@@ -87,118 +124,179 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
     const int64_t warp_global = (int64_t)blockIdx.x * wpb + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * wpb;
     const bool weighted = a.estimate_type == 3;
+    const double beta = a.beta;
 
     for (int64_t t = warp_global; t < n_tiles; t += warp_stride) {
         const int64_t i_raw = (t << 5) + lane;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;
+
+        // pull the next tile of this warp towards L2 while this one is processed
+        {
+            const int64_t t2 = t + warp_stride;
+            if (t2 < n_tiles) {
+                const int64_t i2 = t2 << 5;
+                for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (q >> 1) * ld + i2 + (q & 1) * 16);
+                for (int q = lane; q < 2 * D; q += 32) prefetch_l2(a.X_soa + (q >> 1) * ld + i2 + (q & 1) * 16);
+                for (int q = lane; q < 2 * W; q += 32) prefetch_l2(a.nbr_w + (q >> 1) * ld + i2 + (q & 1) * 16);
+                for (int q = lane; q < W; q += 32) prefetch_l2(a.nbr_id + q * ld + i2);
+            }
+        }
+
         const int li = a.labels[a.own_offset + i];
+        const int pos_li = (li / TK) * TKs + (li % TK);
+        const double lp_li = a.logp[li * ld + i];
 
         // ---------------- node phase ----------------
-        double pmin = 0.0;  // min_k pp_k (stabilises the pairwise soft-max)
-        double pc = 0.0;
-        double wtot = 0.0;
-        if (a.potts) {
-            for (int c = 0; c < rsp; c += 2) *reinterpret_cast<double2 *>(Prow + c) = make_double2(0.0, 0.0);
-            double smax = 0.0;
-            int deg = 0;
-            for (int s = 0; s < W; ++s) {
-                const int j = a.nbr_id[s * ld + i];
-                if (j >= 0) {
-                    const int lj = a.labels[j];
-                    const double bw = weighted ? a.beta * a.nbr_w[s * ld + i] : a.beta;
-                    const int pos = (lj / TK) * TKs + (lj % TK);
-                    const double v = Prow[pos] + bw;
-                    Prow[pos] = v;
-                    smax = fmax(smax, v);
-                    wtot += bw;
-                    pc += (lj != li) ? bw : 0.0;
-                    ++deg;
+        double pc = 0.0, pwn_log = 0.0, esum = 0.0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            double wtot = 0.0, pmin = 0.0, qsum = 1.0, pp_li;
+            pc = 0.0;
+            if (a.potts) {
+#pragma unroll 4
+                for (int c = 0; c < rsp; c += 2) *reinterpret_cast<double2 *>(Prow + c) = make_double2(0.0, 0.0);
+                double smax = 0.0;
+                int deg = 0;
+                for (int s = 0; s < W; ++s) {
+                    const int j = a.nbr_id[s * ld + i];
+                    if (j >= 0) {
+                        const int lj = a.labels[j];
+                        const double bw = weighted ? beta * a.nbr_w[s * ld + i] : beta;
+                        const int pos = (lj / TK) * TKs + (lj % TK);
+                        const double v = Prow[pos] + bw;
+                        Prow[pos] = v;
+                        smax = fmax(smax, v);
+                        wtot += bw;
+                        pc += (lj != li) ? bw : 0.0;
+                        ++deg;
+                    }
                 }
-            }
-            if (deg == 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
-                wtot = a.beta;
-                Prow[(li / TK) * TKs + (li % TK)] = a.beta;
-                smax = a.beta;
-            }
-            // some state is absent among the neighbours unless one label carries every slot
-            pmin = wtot - smax;
-        } else {
-            int deg = 0;
-            for (int s = 0; s < W; ++s) deg += a.nbr_id[s * ld + i] >= 0;
-            pmin = INFINITY;
-            for (int k = 0; k < K; ++k) {
-                double pp = 0.0;
-                if (deg == 0) {
-                    pp = a.V[li * K + k];
-                } else {
+                if (deg == 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
+                    wtot = beta;
+                    Prow[pos_li] = beta;
+                    smax = beta;
+                }
+                const double s_li = Prow[pos_li];
+                pp_li = wtot - s_li;
+                pmin = wtot - smax;
+                if (first_pass) {
+                    // soft-max of -pp over the states: K - m states carry pp = wtot, the m labels
+                    // seen among the neighbours carry wtot - S.  A counted S is flagged by its sign.
+                    double qs = 0.0;
+                    int m = 0;
                     for (int s = 0; s < W; ++s) {
                         const int j = a.nbr_id[s * ld + i];
-                        if (j >= 0) {
-                            const double ws = weighted ? a.nbr_w[s * ld + i] : 1.0;
-                            pp += a.V[a.labels[j] * K + k] * ws;
+                        const int lj = j >= 0 ? a.labels[j] : li;
+                        const int pos = (lj / TK) * TKs + (lj % TK);
+                        const double v = Prow[pos];
+                        const bool first = j >= 0 && v > 0.0;
+                        if (__any_sync(0xffffffffu, first)) {
+                            const double e = exp(v - smax);
+                            if (first) {
+                                qs += e;
+                                ++m;
+                                Prow[pos] = -v;
+                            }
+                        }
+                    }
+                    if (deg == 0) {
+                        qs = 1.0;
+                        m = 1;
+                    }
+                    qsum = qs + (double)(K - m) * exp(-smax);
+                    pwn_log = log(exp(s_li - smax) / qsum + 1e-16);
+                }
+            } else {
+                int deg = 0;
+                for (int s = 0; s < W; ++s) deg += a.nbr_id[s * ld + i] >= 0;
+                pmin = INFINITY;
+                pp_li = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    double pp = 0.0;
+                    if (deg == 0) {
+                        pp = a.V[li * K + k];
+                    } else {
+                        for (int s = 0; s < W; ++s) {
+                            const int j = a.nbr_id[s * ld + i];
+                            if (j >= 0) pp += a.V[a.labels[j] * K + k] * (weighted ? a.nbr_w[s * ld + i] : 1.0);
+                        }
+                    }
+                    Prow[(k / TK) * TKs + (k % TK)] = pp;
+                    pmin = fmin(pmin, pp);
+                    if (k == li) pp_li = pp;
+                }
+                for (int s = 0; s < W; ++s) {
+                    const int j = a.nbr_id[s * ld + i];
+                    if (j >= 0) pc += a.V[a.labels[j] * K + li] * (weighted ? a.nbr_w[s * ld + i] : 1.0);
+                }
+                if (first_pass) {
+                    qsum = 0.0;
+                    for (int k = 0; k < K; ++k) qsum += exp(pmin - Prow[(k / TK) * TKs + (k % TK)]);
+                    pwn_log = log(exp(pmin - pp_li) / qsum + 1e-16);
+                }
+            }
+
+            // soft-max shift: the label's own exponent (no maximum pass); the exact maximum is
+            // only computed on the retry after an overflow.
+            double shift = lp_li - pp_li;
+            if (attempt == 1) {
+                double amax = -INFINITY;
+                for (int ktile = 0; ktile < nkt_total; ++ktile) {
+#pragma unroll
+                    for (int ii = 0; ii < TK; ++ii) {
+                        const int k = ktile * TK + ii;
+                        if (k < K) {
+                            const double sv = Prow[ktile * TKs + ii];
+                            const double pp = a.potts ? wtot - fabs(sv) : sv;
+                            amax = fmax(amax, a.logp[k * ld + i] - pp);
                         }
                     }
                 }
-                Prow[(k / TK) * TKs + (k % TK)] = pp;
-                pmin = fmin(pmin, pp);
+                shift = amax;
             }
-            for (int s = 0; s < W; ++s) {
-                const int j = a.nbr_id[s * ld + i];
-                if (j >= 0) pc += a.V[a.labels[j] * K + li] * (weighted ? a.nbr_w[s * ld + i] : 1.0);
+
+            // fused pass: e_k = exp(logp_k - pp_k - shift), normaliser, optional pp output
+            esum = 0.0;
+#pragma unroll 2
+            for (int ktile = 0; ktile < nkt_total; ++ktile) {
+                double sv[TKs], lp[TK];
+#pragma unroll
+                for (int c = 0; c < TKs; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(Prow + ktile * TKs + c);
+                    sv[c] = v.x;
+                    sv[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii) {
+                    const int k = ktile * TK + ii;
+                    lp[ii] = k < K ? a.logp[k * ld + i] : 0.0;
+                }
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii) {
+                    const int k = ktile * TK + ii;
+                    const double pp = a.potts ? wtot - fabs(sv[ii]) : sv[ii];
+                    double e = 0.0;
+                    if (k < K) {
+                        e = exp((lp[ii] - pp) - shift);
+                        if (a.pp_soa != nullptr && first_pass && valid) a.pp_soa[k * ld + i] = pp;
+                    }
+                    esum += e;
+                    sv[ii] = e;
+                }
+                if (TK < TKs) sv[TKs - 1] = 0.0;
+#pragma unroll
+                for (int c = 0; c < TKs; c += 2)
+                    *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(sv[c], sv[c + 1]);
             }
+            const bool bad = !(esum <= DBL_MAX);
+            if (!__any_sync(0xffffffffu, bad)) break;
         }
 
-        // pass 1: a_k = logp_k - pp_k, its maximum, and the pairwise soft-max normaliser
-        double amax = -INFINITY, qsum = 0.0, a_li = 0.0, pp_li = 0.0;
-        const double q0 = exp(pmin - wtot);  // Potts: exp(-(pp - pmin)) of a state no neighbour carries
-        for (int ktile = 0; ktile < nkt_total; ++ktile) {
-#pragma unroll
-            for (int ii = 0; ii < TK; ++ii) {
-                const int k = ktile * TK + ii;
-                if (k < K) {
-                    const int pos = ktile * TKs + ii;
-                    const double sv = Prow[pos];
-                    double pp, q;
-                    if (a.potts) {
-                        pp = wtot - sv;
-                        const bool touched = sv != 0.0;
-                        q = q0;
-                        if (__any_sync(0xffffffffu, touched)) q = touched ? exp(pmin - pp) : q0;
-                    } else {
-                        pp = sv;
-                        q = exp(pmin - pp);
-                    }
-                    qsum += q;
-                    if (a.pp_soa != nullptr && first_pass && valid) a.pp_soa[k * ld + i] = pp;
-                    const double lp = a.logp[k * ld + i];
-                    const double ak = lp - pp;
-                    if (k == li) {
-                        a_li = lp;
-                        pp_li = pp;
-                    }
-                    Prow[pos] = ak;
-                    amax = fmax(amax, ak);
-                } else {
-                    if (ii < TKs) Prow[ktile * TKs + ii] = -INFINITY;
-                }
-            }
-            if (TK < TKs) Prow[ktile * TKs + TK] = -INFINITY;
-        }
-        // pass 2: e_k = exp(a_k - amax), normaliser
-        double esum = 0.0;
-        for (int c = 0; c < nkt_total * TKs; c += 2) {
-            double2 v = *reinterpret_cast<double2 *>(Prow + c);
-            v.x = exp(v.x - amax);
-            v.y = exp(v.y - amax);
-            esum += v.x + v.y;
-            *reinterpret_cast<double2 *>(Prow + c) = v;
-        }
         const double inv = valid ? 1.0 / esum : 0.0;
         if (first_pass && valid) {
             c_pair += pc;
-            c_un += a_li;
-            c_pwn += log(exp(pmin - pp_li) / qsum + 1e-16);
+            c_un += lp_li;
+            c_pwn += pwn_log;
             if (a.post_soa != nullptr) {
                 for (int ktile = 0; ktile < nkt_total; ++ktile)
 #pragma unroll
@@ -215,19 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                 x[j] = a.X_soa[j * ld + i];
                 xs[j] = x[j] * inv;
             }
-#pragma unroll
-            for (int c = 0; c < RSY; c += 2) {
-                double2 v = make_double2(0.0, 0.0);
-                {
-                    const int tile0 = c / TFs, off0 = c % TFs;
-                    const int f0 = tile0 * TF + off0;
-                    if (tile0 < NFT && off0 < TF && f0 < F) v.x = feature_value<D>(f0, x, xs, inv);
-                    const int tile1 = (c + 1) / TFs, off1 = (c + 1) % TFs;
-                    const int f1 = tile1 * TF + off1;
-                    if (tile1 < NFT && off1 < TF && f1 < F) v.y = feature_value<D>(f1, x, xs, inv);
-                }
-                *reinterpret_cast<double2 *>(Yrow + c) = v;
-            }
+            write_y_row<D, TF>(Yrow, x, xs, inv, std::make_integer_sequence<int, RSY / 2>{});
         }
         __syncwarp();
 
@@ -240,13 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                 double p[TKs], y[TFs];
 #pragma unroll
                 for (int c = 0; c < TKs; c += 2) {
-                    double2 v = *reinterpret_cast<const double2 *>(pb + nn * rsp + c);
+                    const double2 v = *reinterpret_cast<const double2 *>(pb + nn * rsp + c);
                     p[c] = v.x;
                     p[c + 1] = v.y;
                 }
 #pragma unroll
                 for (int c = 0; c < TFs; c += 2) {
-                    double2 v = *reinterpret_cast<const double2 *>(yb + nn * RSY + c);
+                    const double2 v = *reinterpret_cast<const double2 *>(yb + nn * RSY + c);
                     y[c] = v.x;
                     y[c + 1] = v.y;
                 }
@@ -263,13 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
     __syncthreads();
     double *red = smem;  // K*F + 3 doubles
     const int KF = K * F;
-    if (kt_begin == 0 || true) {
-        for (int e = threadIdx.x; e < KF + 3; e += blockDim.x) red[e] = 0.0;
-    }
+    for (int e = threadIdx.x; e < KF + 3; e += blockDim.x) red[e] = 0.0;
     __syncthreads();
-    const int ns_total = 32 / tiles;
     for (int w = 0; w < wpb; ++w) {
-        for (int s = 0; s < ns_total; ++s) {
+        for (int s = 0; s < NS; ++s) {
             if (warp == w && sub == s && lane_active) {
 #pragma unroll
                 for (int ii = 0; ii < TK; ++ii) {

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read on the CPU box): per kernel duration, pipes, DRAM bytes, stalls.
+usage: scripts_ncu_summary.py gpurun_out/prof_X.ncu-rep"""
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[0]
+KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
+units = rows[1]
+for r in rows[2:]:
+    print("=====", r[hdr.index("Kernel Name")][:100])
+    for k in KEYS:
+        if k in hdr:
+            print("   %-75s %s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+    st = []
+    for h, v in zip(hdr, r):
+        if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
+            try:
+                st.append((float(v), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+            except ValueError:
+                pass
+    print("   stalls (warps per issue-active cycle):", ", ".join("%s=%.2f" % (n, f) for f, n in sorted(st, reverse=True)[:7]))
