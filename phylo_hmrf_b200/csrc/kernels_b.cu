@@ -26,18 +26,37 @@ namespace phmrf {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kFastSlots = 8;  // neighbour slots handled in registers by the fast node phase
 
 __host__ __device__ constexpr int even_up(int v) { return (v + 1) & ~1; }
 // row strides (in doubles) are even (16-byte alignment of every row) with stride/2 odd, so
 // that the 128-bit column accesses of the node phase are bank-conflict free.
 __host__ __device__ constexpr int pad_row(int v) { return (even_up(v) / 2) % 2 == 1 ? even_up(v) : even_up(v) + 2; }
 
+// Stride (in doubles) between the register tiles of one row: the stat phase reads `ntiles`
+// different 16-byte chunks of a row in one LDS.128, which is conflict free when the chunk
+// starts are at least 4 banks apart modulo 32.
+__host__ __device__ constexpr bool stride_ok(int S, int ntiles) {
+    for (int t1 = 0; t1 < ntiles; ++t1)
+        for (int t2 = t1 + 1; t2 < ntiles; ++t2) {
+            const int dd = ((t2 - t1) * S * 2) % 32;
+            if (dd < 4 || dd > 28) return false;
+        }
+    return true;
+}
+__host__ __device__ constexpr int tile_stride(int T, int ntiles) {
+    for (int S = even_up(T); S <= even_up(T) + 16; S += 2)
+        if (stride_ok(S, ntiles)) return S;
+    return even_up(T);
+}
+
 template <int D, int TK, int TF>
 struct Cfg {
     static constexpr int F = n_stat_features(D);
-    static constexpr int TKs = even_up(TK);
-    static constexpr int TFs = even_up(TF);
     static constexpr int NFT = (F + TF - 1) / TF;
+    static constexpr int NKT_MAX = 32 / NFT;
+    static constexpr int TKs = tile_stride(TK, NKT_MAX);
+    static constexpr int TFs = tile_stride(TF, NFT);
     static constexpr int RSY = pad_row(NFT * TFs);
 };
 
@@ -60,9 +79,8 @@ __host__ __device__ constexpr int tri_col_of(int r, int D) {
 }
 
 // value stored at position POS of the Y row: feature f = tile*TF + off, or 0 on padding.
-template <int D, int TF, int POS>
+template <int D, int TF, int TFs, int POS>
 __device__ __forceinline__ double y_at(const double (&x)[D], const double (&xs)[D], double inv) {
-    constexpr int TFs = even_up(TF);
     constexpr int F = n_stat_features(D);
     constexpr int NFT = (F + TF - 1) / TF;
     constexpr int tile = POS / TFs, off = POS % TFs;
@@ -79,15 +97,48 @@ __device__ __forceinline__ double y_at(const double (&x)[D], const double (&xs)[
     }
 }
 
-template <int D, int TF, int... Cs>
+template <int D, int TF, int TFs, int... Cs>
 __device__ __forceinline__ void write_y_row(double *Yrow, const double (&x)[D], const double (&xs)[D], double inv,
                                             std::integer_sequence<int, Cs...>) {
     ((*reinterpret_cast<double2 *>(Yrow + 2 * Cs) =
-          make_double2(y_at<D, TF, 2 * Cs>(x, xs, inv), y_at<D, TF, 2 * Cs + 1>(x, xs, inv))),
+          make_double2(y_at<D, TF, TFs, 2 * Cs>(x, xs, inv), y_at<D, TF, TFs, 2 * Cs + 1>(x, xs, inv))),
      ...);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// exp() for the soft-max terms: round-to-nearest range reduction with the 2^52+2^51 magic
+// constant, two-term ln2, degree-11 polynomial on |r| <= ln2/2 (truncation error < 7e-15
+// relative), exponent patched in with integer adds.  Results below 2^-1021 flush to 0 and
+// arguments beyond the double range return +inf; no branches, ~15 FP64-pipe instructions
+// (libdevice exp() measured ~50 instructions per call here, mostly range handling).
+__device__ __forceinline__ double exp_sm(double t) {
+    const double kMagic = 6755399441055744.0;
+    const double s = fma(t, 1.4426950408889634, kMagic);
+    const int n = __double2loint(s);
+    const double fn = s - kMagic;
+    double r = fma(fn, -6.93147180559945286e-01, t);
+    r = fma(fn, -2.31904681384629956e-17, r);
+    double p = 2.50521083854417188e-08;               // 1/11!
+    p = fma(p, r, 2.75573192239858907e-07);           // 1/10!
+    p = fma(p, r, 2.75573192239858907e-06);           // 1/9!
+    p = fma(p, r, 2.48015873015873016e-05);           // 1/8!
+    p = fma(p, r, 1.98412698412698413e-04);           // 1/7!
+    p = fma(p, r, 1.38888888888888894e-03);           // 1/6!
+    p = fma(p, r, 8.33333333333333322e-03);           // 1/5!
+    p = fma(p, r, 4.16666666666666644e-02);           // 1/4!
+    p = fma(p, r, 1.66666666666666657e-01);           // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int hi = __double2hiint(p) + n * 1048576;
+    int lo = __double2loint(p);
+    const bool under = n < -1021;
+    const bool over = n > 1023;
+    hi = under ? 0 : (over ? 0x7ff00000 : hi);
+    lo = (under || over) ? 0 : lo;
+    return __hiloint2double(hi, lo);
+}
 
 template <int D, int TK, int TF>
 __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt_total, int kt_begin, int nkt_pass,
@@ -125,6 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
     const int64_t warp_stride = (int64_t)gridDim.x * wpb;
     const bool weighted = a.estimate_type == 3;
     const double beta = a.beta;
+    const bool fast_ok = a.potts && W <= kFastSlots && a.pp_soa == nullptr;
 
     for (int64_t t = warp_global; t < n_tiles; t += warp_stride) {
         const int64_t i_raw = (t << 5) + lane;
@@ -149,11 +201,111 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
 
         // ---------------- node phase ----------------
         double pc = 0.0, pwn_log = 0.0, esum = 0.0;
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        bool need_exact = !fast_ok;
+        if (fast_ok) {
+            // Potts compatibility, <= 8 neighbour slots: everything neighbour-related stays in
+            // registers.  With S_c = sum of beta*w over the neighbours carrying label c,
+            //   pp_k = wtot - S_k,   exp(logp_k - pp_k - shift) = exp(logp_k - c0) * exp(S_k),
+            // c0 = logp_li + S_li, so the K-wide pass needs no per-state neighbour data and the
+            // <= 8 distinct neighbour labels are patched afterwards with f_c = exp(S_c).
+            int lab[kFastSlots];
+            double sw[kFastSlots];
+            bool live[kFastSlots];
+            {
+                int jid[kFastSlots];
+#pragma unroll
+                for (int s = 0; s < kFastSlots; ++s) jid[s] = s < W ? a.nbr_id[s * ld + i] : -1;
+#pragma unroll
+                for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1 - s;
+#pragma unroll
+                for (int s = 0; s < kFastSlots; ++s) {
+                    sw[s] = 0.0;
+                    if (jid[s] >= 0) sw[s] = weighted ? beta * a.nbr_w[s * ld + i] : beta;
+                    live[s] = jid[s] >= 0;
+                }
+            }
+            bool any_nbr = false;
+#pragma unroll
+            for (int s = 0; s < kFastSlots; ++s) {
+                any_nbr |= live[s];
+                pc += (live[s] && lab[s] != li) ? sw[s] : 0.0;
+            }
+            if (!any_nbr) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
+                lab[0] = li;
+                sw[0] = beta;
+                live[0] = true;
+            }
+            // fold duplicate labels into their first occurrence
+#pragma unroll
+            for (int s = 1; s < kFastSlots; ++s)
+#pragma unroll
+                for (int q = 0; q < s; ++q) {
+                    const bool dup = live[s] && live[q] && lab[q] == lab[s];
+                    sw[q] += dup ? sw[s] : 0.0;
+                    live[s] = live[s] && !dup;
+                }
+            double s_li = 0.0, fsum = 0.0, f_li = 1.0;
+            double f[kFastSlots];
+            int m = 0;
+#pragma unroll
+            for (int s = 0; s < kFastSlots; ++s) {
+                f[s] = 1.0;
+                if (__any_sync(0xffffffffu, live[s])) {
+                    const double e = exp_sm(sw[s]);
+                    if (live[s]) {
+                        f[s] = e;
+                        fsum += e;
+                        ++m;
+                        if (lab[s] == li) {
+                            s_li = sw[s];
+                            f_li = e;
+                        }
+                    }
+                }
+            }
+            // soft-max of -pp at the node's own label: exp(S_li) / (sum_c exp(S_c) + (K - m))
+            pwn_log = log(f_li / (fsum + (double)(K - m)) + 1e-16);
+            const double c0 = lp_li + s_li;
+#pragma unroll 2
+            for (int ktile = 0; ktile < nkt_total; ++ktile) {
+                double e[TKs];
+#pragma unroll
+                for (int ii = 0; ii < TKs; ++ii) e[ii] = 0.0;
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii) {
+                    const int k = ktile * TK + ii;
+                    if (k < K) e[ii] = a.logp[k * ld + i];
+                }
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii) {
+                    const int k = ktile * TK + ii;
+                    e[ii] = k < K ? exp_sm(e[ii] - c0) : 0.0;
+                    esum += e[ii];
+                }
+#pragma unroll
+                for (int c = 0; c < TKs; c += 2)
+                    *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(e[c], e[c + 1]);
+            }
+#pragma unroll
+            for (int s = 0; s < kFastSlots; ++s) {
+                if (__any_sync(0xffffffffu, live[s])) {
+                    if (live[s]) {
+                        const int pos = (lab[s] / TK) * TKs + (lab[s] % TK);
+                        const double e_old = Prow[pos];
+                        const double e_new = e_old * f[s];
+                        Prow[pos] = e_new;
+                        esum += e_new - e_old;
+                    }
+                }
+            }
+            const bool bad = !(esum <= DBL_MAX) || !(fsum <= DBL_MAX);
+            need_exact = __any_sync(0xffffffffu, bad);
+        }
+        if (need_exact) {
+            // General path: any compatibility matrix, any degree, exact soft-max maximum.
             double wtot = 0.0, pmin = 0.0, qsum = 1.0, pp_li;
             pc = 0.0;
             if (a.potts) {
-#pragma unroll 4
                 for (int c = 0; c < rsp; c += 2) *reinterpret_cast<double2 *>(Prow + c) = make_double2(0.0, 0.0);
                 double smax = 0.0;
                 int deg = 0;
@@ -171,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                         ++deg;
                     }
                 }
-                if (deg == 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
+                if (deg == 0) {
                     wtot = beta;
                     Prow[pos_li] = beta;
                     smax = beta;
@@ -180,8 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                 pp_li = wtot - s_li;
                 pmin = wtot - smax;
                 if (first_pass) {
-                    // soft-max of -pp over the states: K - m states carry pp = wtot, the m labels
-                    // seen among the neighbours carry wtot - S.  A counted S is flagged by its sign.
+                    // K - m states carry pp = wtot, the m labels seen among the neighbours carry
+                    // wtot - S; a counted S is flagged by flipping its sign.
                     double qs = 0.0;
                     int m = 0;
                     for (int s = 0; s < W; ++s) {
@@ -189,14 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                         const int lj = j >= 0 ? a.labels[j] : li;
                         const int pos = (lj / TK) * TKs + (lj % TK);
                         const double v = Prow[pos];
-                        const bool first = j >= 0 && v > 0.0;
-                        if (__any_sync(0xffffffffu, first)) {
-                            const double e = exp(v - smax);
-                            if (first) {
-                                qs += e;
-                                ++m;
-                                Prow[pos] = -v;
-                            }
+                        if (j >= 0 && v > 0.0) {
+                            qs += exp(v - smax);
+                            ++m;
+                            Prow[pos] = -v;
                         }
                     }
                     if (deg == 0) {
@@ -235,61 +383,34 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                     pwn_log = log(exp(pmin - pp_li) / qsum + 1e-16);
                 }
             }
-
-            // soft-max shift: the label's own exponent (no maximum pass); the exact maximum is
-            // only computed on the retry after an overflow.
-            double shift = lp_li - pp_li;
-            if (attempt == 1) {
-                double amax = -INFINITY;
-                for (int ktile = 0; ktile < nkt_total; ++ktile) {
+            double amax = -INFINITY;
+            for (int ktile = 0; ktile < nkt_total; ++ktile) {
 #pragma unroll
-                    for (int ii = 0; ii < TK; ++ii) {
-                        const int k = ktile * TK + ii;
-                        if (k < K) {
-                            const double sv = Prow[ktile * TKs + ii];
-                            const double pp = a.potts ? wtot - fabs(sv) : sv;
-                            amax = fmax(amax, a.logp[k * ld + i] - pp);
-                        }
+                for (int ii = 0; ii < TK; ++ii) {
+                    const int k = ktile * TK + ii;
+                    if (k < K) {
+                        const double sv = Prow[ktile * TKs + ii];
+                        const double pp = a.potts ? wtot - fabs(sv) : sv;
+                        amax = fmax(amax, a.logp[k * ld + i] - pp);
                     }
                 }
-                shift = amax;
             }
-
-            // fused pass: e_k = exp(logp_k - pp_k - shift), normaliser, optional pp output
             esum = 0.0;
-#pragma unroll 2
             for (int ktile = 0; ktile < nkt_total; ++ktile) {
-                double sv[TKs], lp[TK];
 #pragma unroll
-                for (int c = 0; c < TKs; c += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(Prow + ktile * TKs + c);
-                    sv[c] = v.x;
-                    sv[c + 1] = v.y;
-                }
-#pragma unroll
-                for (int ii = 0; ii < TK; ++ii) {
+                for (int ii = 0; ii < TKs; ++ii) {
                     const int k = ktile * TK + ii;
-                    lp[ii] = k < K ? a.logp[k * ld + i] : 0.0;
-                }
-#pragma unroll
-                for (int ii = 0; ii < TK; ++ii) {
-                    const int k = ktile * TK + ii;
-                    const double pp = a.potts ? wtot - fabs(sv[ii]) : sv[ii];
                     double e = 0.0;
-                    if (k < K) {
-                        e = exp((lp[ii] - pp) - shift);
+                    if (ii < TK && k < K) {
+                        const double sv = Prow[ktile * TKs + ii];
+                        const double pp = a.potts ? wtot - fabs(sv) : sv;
+                        e = exp((a.logp[k * ld + i] - pp) - amax);
                         if (a.pp_soa != nullptr && first_pass && valid) a.pp_soa[k * ld + i] = pp;
                     }
                     esum += e;
-                    sv[ii] = e;
+                    Prow[ktile * TKs + ii] = e;
                 }
-                if (TK < TKs) sv[TKs - 1] = 0.0;
-#pragma unroll
-                for (int c = 0; c < TKs; c += 2)
-                    *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(sv[c], sv[c + 1]);
             }
-            const bool bad = !(esum <= DBL_MAX);
-            if (!__any_sync(0xffffffffu, bad)) break;
         }
 
         const double inv = valid ? 1.0 / esum : 0.0;
@@ -313,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                 x[j] = a.X_soa[j * ld + i];
                 xs[j] = x[j] * inv;
             }
-            write_y_row<D, TF>(Yrow, x, xs, inv, std::make_integer_sequence<int, RSY / 2>{});
+            write_y_row<D, TF, TFs>(Yrow, x, xs, inv, std::make_integer_sequence<int, RSY / 2>{});
         }
         __syncwarp();
 
@@ -323,15 +444,15 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
             const double *yb = Ys + ft * TFs;
 #pragma unroll 2
             for (int nn = sub; nn < 32; nn += NS) {
-                double p[TKs], y[TFs];
+                double p[even_up(TK)], y[even_up(TF)];
 #pragma unroll
-                for (int c = 0; c < TKs; c += 2) {
+                for (int c = 0; c < even_up(TK); c += 2) {
                     const double2 v = *reinterpret_cast<const double2 *>(pb + nn * rsp + c);
                     p[c] = v.x;
                     p[c + 1] = v.y;
                 }
 #pragma unroll
-                for (int c = 0; c < TFs; c += 2) {
+                for (int c = 0; c < even_up(TF); c += 2) {
                     const double2 v = *reinterpret_cast<const double2 *>(yb + nn * RSY + c);
                     y[c] = v.x;
                     y[c + 1] = v.y;
