@@ -61,6 +61,7 @@ struct phmrf_region {
     long long bcap = 0;
     double *d_partials = nullptr;
     double *d_stats = nullptr;
+    int *d_flags = nullptr;
     double *d_scratch = nullptr;  // [K][ld] posteriors / AoS staging, allocated on demand
     int64_t scratch_elems = 0;
     bool have_logp = false, have_unary = false, have_labels = false;
@@ -303,6 +304,7 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
     TRY(dev_alloc(r, &r->d_blist, r->bcap));
     TRY(dev_alloc(r, &r->d_partials, (int64_t)ctx->sm_count * ((int64_t)K * F + 3)));
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
+    TRY(dev_alloc(r, &r->d_flags, 1));
 
     // X: upload row-major, transpose on the device into the feature-major layout
     if (n_own > 0) {
@@ -389,6 +391,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     cudaFree(r->d_blist);
     cudaFree(r->d_partials);
     cudaFree(r->d_stats);
+    cudaFree(r->d_flags);
     cudaFree(r->d_scratch);
     if (r->own_stream) cudaStreamDestroy(r->stream);
     cudaGetLastError();
@@ -542,7 +545,8 @@ int phmrf_labels_argmin_unary(phmrf_region *r, int32_t *labels_out) {
     return PHMRF_OK;
 }
 
-static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, bool want_pp = false) {
+static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, bool want_pp = false,
+                         bool force_general = false) {
     if (!r) return PHMRF_E_INVALID;
     if (!r->have_logp || !r->have_labels) {
         set_error("phmrf_estep_stats: needs phmrf_emit_loglik and labels first");
@@ -576,6 +580,9 @@ static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, boo
     }
     a.partials = r->d_partials;
     a.stats_out = r->d_stats;
+    a.flags = r->d_flags;
+    a.force_general = force_general ? 1 : 0;
+    PHMRF_CUDA(cudaMemsetAsync(r->d_flags, 0, sizeof(int), r->stream));
     return launch_estep(a, ctx->sm_count, r->stream);
 }
 
@@ -589,13 +596,21 @@ int phmrf_estep_stats(phmrf_region *r, int estimate_type, double *post_out, doub
     const int K = ctx->K;
     const int64_t len = phmrf_stats_len(ctx);
     std::vector<double> host((size_t)len);
-    if (post_out && r->n > 0) {
-        double *aos = r->d_scratch + (int64_t)K * r->ld;
-        if ((rc = launch_soa_to_aos(r->d_scratch, aos, r->n, K, r->ld, r->stream)) != PHMRF_OK) return rc;
-        PHMRF_CUDA(cudaMemcpyAsync(post_out, aos, sizeof(double) * r->n * K, cudaMemcpyDeviceToHost, r->stream));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int flag = 0;
+        if (post_out && r->n > 0) {
+            double *aos = r->d_scratch + (int64_t)K * r->ld;
+            if ((rc = launch_soa_to_aos(r->d_scratch, aos, r->n, K, r->ld, r->stream)) != PHMRF_OK) return rc;
+            PHMRF_CUDA(cudaMemcpyAsync(post_out, aos, sizeof(double) * r->n * K, cudaMemcpyDeviceToHost, r->stream));
+        }
+        PHMRF_CUDA(cudaMemcpyAsync(host.data(), r->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, r->stream));
+        PHMRF_CUDA(cudaMemcpyAsync(&flag, r->d_flags, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+        PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+        if (!(flag & 1) || attempt == 1) break;
+        // the pipeline kernel met a soft-max overflow (only reachable with extreme beta):
+        // redo the region on the general kernel, which uses the exact maximum
+        if ((rc = estep_enqueue(r, estimate_type, post_out != nullptr, false, true)) != PHMRF_OK) return rc;
     }
-    PHMRF_CUDA(cudaMemcpyAsync(host.data(), r->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, r->stream));
-    PHMRF_CUDA(cudaStreamSynchronize(r->stream));
     if (stats_out) std::memcpy(stats_out, host.data(), sizeof(double) * (len - 3));
     if (cost_sums_out) std::memcpy(cost_sums_out, host.data() + (len - 3), sizeof(double) * 3);
     return PHMRF_OK;

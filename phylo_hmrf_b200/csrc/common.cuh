@@ -68,10 +68,16 @@ struct EstepArgs {
     double *pp_soa;           // nullable [K][ld] pairwise potential (signature-parity output)
     double *partials;         // [grid][K*F + 4] per-block partial sums
     double *stats_out;        // [K*(1+D+D*D) + 3]
+    int *flags;               // [1] device flag: bit 0 = the pipeline met an overflow, rerun on the general path
+    int force_general;        // skip the pipeline kernel
 };
 // Returns the grid size it will use (for sizing `partials`) when args == nullptr.
 int estep_grid(int D, int K, int sm_count);
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s);
+// Warp-specialised pipeline (kernels_b2.cu); *handled=false when the shape is outside its range.
+int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);
+// Fold per-block partials into stats_out (defined in kernels_b.cu).
+int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, double *stats_out, cudaStream_t s);
 
 // ---- probes (probe.cu) ----------------------------------------------------------------
 int run_probe(int which, double *out);

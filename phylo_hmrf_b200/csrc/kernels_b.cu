@@ -16,129 +16,13 @@
 // Accumulators live in registers for the whole kernel; block partials are reduced in a
 // fixed order (deterministic) and a final kernel folds them and unpacks the symmetric
 // scatter into the reference's [K], [K,d], [K,d,d] layout.
-#include <cfloat>
-#include <utility>
-
-#include "common.cuh"
+#include "estep_common.cuh"
 
 namespace phmrf {
 
+using namespace estep;
+
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kFastSlots = 8;  // neighbour slots handled in registers by the fast node phase
-
-__host__ __device__ constexpr int even_up(int v) { return (v + 1) & ~1; }
-// row strides (in doubles) are even (16-byte alignment of every row) with stride/2 odd, so
-// that the 128-bit column accesses of the node phase are bank-conflict free.
-__host__ __device__ constexpr int pad_row(int v) { return (even_up(v) / 2) % 2 == 1 ? even_up(v) : even_up(v) + 2; }
-
-// Stride (in doubles) between the register tiles of one row: the stat phase reads `ntiles`
-// different 16-byte chunks of a row in one LDS.128, which is conflict free when the chunk
-// starts are at least 4 banks apart modulo 32.
-__host__ __device__ constexpr bool stride_ok(int S, int ntiles) {
-    for (int t1 = 0; t1 < ntiles; ++t1)
-        for (int t2 = t1 + 1; t2 < ntiles; ++t2) {
-            const int dd = ((t2 - t1) * S * 2) % 32;
-            if (dd < 4 || dd > 28) return false;
-        }
-    return true;
-}
-__host__ __device__ constexpr int tile_stride(int T, int ntiles) {
-    for (int S = even_up(T); S <= even_up(T) + 16; S += 2)
-        if (stride_ok(S, ntiles)) return S;
-    return even_up(T);
-}
-
-template <int D, int TK, int TF>
-struct Cfg {
-    static constexpr int F = n_stat_features(D);
-    static constexpr int NFT = (F + TF - 1) / TF;
-    static constexpr int NKT_MAX = 32 / NFT;
-    static constexpr int TKs = tile_stride(TK, NKT_MAX);
-    static constexpr int TFs = tile_stride(TF, NFT);
-    static constexpr int RSY = pad_row(NFT * TFs);
-};
-
-// ---- per-node feature row, resolved at compile time ------------------------------------
-__host__ __device__ constexpr int tri_row_of(int r, int D) {
-    int i = 0;
-    while (r >= D - i) {
-        r -= D - i;
-        ++i;
-    }
-    return i;
-}
-__host__ __device__ constexpr int tri_col_of(int r, int D) {
-    int i = 0;
-    while (r >= D - i) {
-        r -= D - i;
-        ++i;
-    }
-    return i + r;
-}
-
-// value stored at position POS of the Y row: feature f = tile*TF + off, or 0 on padding.
-template <int D, int TF, int TFs, int POS>
-__device__ __forceinline__ double y_at(const double (&x)[D], const double (&xs)[D], double inv) {
-    constexpr int F = n_stat_features(D);
-    constexpr int NFT = (F + TF - 1) / TF;
-    constexpr int tile = POS / TFs, off = POS % TFs;
-    constexpr int f = tile * TF + off;
-    if constexpr (tile >= NFT || off >= TF || f >= F) {
-        return 0.0;
-    } else if constexpr (f == 0) {
-        return inv;
-    } else if constexpr (f <= D) {
-        return xs[f - 1];
-    } else {
-        constexpr int r = f - 1 - D;
-        return xs[tri_row_of(r, D)] * x[tri_col_of(r, D)];
-    }
-}
-
-template <int D, int TF, int TFs, int... Cs>
-__device__ __forceinline__ void write_y_row(double *Yrow, const double (&x)[D], const double (&xs)[D], double inv,
-                                            std::integer_sequence<int, Cs...>) {
-    ((*reinterpret_cast<double2 *>(Yrow + 2 * Cs) =
-          make_double2(y_at<D, TF, TFs, 2 * Cs>(x, xs, inv), y_at<D, TF, TFs, 2 * Cs + 1>(x, xs, inv))),
-     ...);
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// exp() for the soft-max terms: round-to-nearest range reduction with the 2^52+2^51 magic
-// constant, two-term ln2, degree-11 polynomial on |r| <= ln2/2 (truncation error < 7e-15
-// relative), exponent patched in with integer adds.  Results below 2^-1021 flush to 0 and
-// arguments beyond the double range return +inf; no branches, ~15 FP64-pipe instructions
-// (libdevice exp() measured ~50 instructions per call here, mostly range handling).
-__device__ __forceinline__ double exp_sm(double t) {
-    const double kMagic = 6755399441055744.0;
-    const double s = fma(t, 1.4426950408889634, kMagic);
-    const int n = __double2loint(s);
-    const double fn = s - kMagic;
-    double r = fma(fn, -6.93147180559945286e-01, t);
-    r = fma(fn, -2.31904681384629956e-17, r);
-    double p = 2.50521083854417188e-08;               // 1/11!
-    p = fma(p, r, 2.75573192239858907e-07);           // 1/10!
-    p = fma(p, r, 2.75573192239858907e-06);           // 1/9!
-    p = fma(p, r, 2.48015873015873016e-05);           // 1/8!
-    p = fma(p, r, 1.98412698412698413e-04);           // 1/7!
-    p = fma(p, r, 1.38888888888888894e-03);           // 1/6!
-    p = fma(p, r, 8.33333333333333322e-03);           // 1/5!
-    p = fma(p, r, 4.16666666666666644e-02);           // 1/4!
-    p = fma(p, r, 1.66666666666666657e-01);           // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    int hi = __double2hiint(p) + n * 1048576;
-    int lo = __double2loint(p);
-    const bool under = n < -1021;
-    const bool over = n > 1023;
-    hi = under ? 0 : (over ? 0x7ff00000 : hi);
-    lo = (under || over) ? 0 : lo;
-    return __hiloint2double(hi, lo);
-}
 
 template <int D, int TK, int TF>
 __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt_total, int kt_begin, int nkt_pass,
@@ -547,28 +431,6 @@ __global__ void estep_finalize_kernel(const double *__restrict__ partials, int n
     }
 }
 
-struct TileChoice {
-    int tk, tf;
-};
-
-// One (TK,TF) register tile per feature count; TF*NFT >= F with little waste, TK*TF <= 60.
-constexpr TileChoice tile_for(int D) {
-    switch (D) {
-        case 1: return {8, 3};
-        case 2: return {8, 6};
-        case 3: return {5, 10};
-        case 4: return {6, 8};
-        case 5: return {5, 11};
-        case 6: return {4, 14};
-        case 7: return {5, 12};
-        case 8: return {4, 15};
-        case 9: return {5, 11};
-        case 10: return {5, 11};
-        case 11: return {4, 13};
-        default: return {4, 13};
-    }
-}
-
 struct Plan {
     int nkt_total, nkt_pass, n_pass, rsp, wpb, grid;
     size_t smem;
@@ -613,13 +475,17 @@ int launch_estep_d(const EstepArgs &a, int sm_count, cudaStream_t s) {
         count_launch();
         PHMRF_CUDA(cudaGetLastError());
     }
-    estep_finalize_kernel<<<8, 256, 0, s>>>(a.partials, p.grid, a.K, D, a.stats_out);
+    return launch_estep_finalize(a.partials, p.grid, a.K, D, a.stats_out, s);
+}
+
+}  // namespace
+
+int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, double *stats_out, cudaStream_t s) {
+    estep_finalize_kernel<<<8, 256, 0, s>>>(partials, n_blocks, K, D, stats_out);
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     return PHMRF_OK;
 }
-
-}  // namespace
 
 int estep_grid(int D, int K, int sm_count) {
     (void)D;
@@ -631,6 +497,11 @@ int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s) {
     if (a.n == 0) {
         PHMRF_CUDA(cudaMemsetAsync(a.stats_out, 0, sizeof(double) * (a.K * (1 + a.D + a.D * a.D) + 3), s));
         return PHMRF_OK;
+    }
+    if (!a.force_general) {
+        bool handled = false;
+        int rc = launch_estep_pipe(a, sm_count, s, &handled);
+        if (rc != PHMRF_OK || handled) return rc;
     }
     switch (a.D) {
 #define PHMRF_CASE(DD) \
