@@ -582,6 +582,7 @@ static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, boo
     a.stats_out = r->d_stats;
     a.flags = r->d_flags;
     a.force_general = force_general ? 1 : 0;
+    a.s_bound = ctx->beta * r->W * (estimate_type == 3 ? r->wmax : 1.0);
     PHMRF_CUDA(cudaMemsetAsync(r->d_flags, 0, sizeof(int), r->stream));
     return launch_estep(a, ctx->sm_count, r->stream);
 }

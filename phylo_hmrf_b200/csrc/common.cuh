@@ -70,6 +70,7 @@ struct EstepArgs {
     double *stats_out;        // [K*(1+D+D*D) + 3]
     int *flags;               // [1] device flag: bit 0 = the pipeline met an overflow, rerun on the general path
     int force_general;        // skip the pipeline kernel
+    double s_bound;           // upper bound of any neighbour weight sum: beta * W * max|w|
 };
 // Returns the grid size it will use (for sizing `partials`) when args == nullptr.
 int estep_grid(int D, int K, int sm_count);

@@ -34,6 +34,61 @@ __host__ __device__ constexpr int tile_stride(int T, int ntiles) {
     return even_up(T);
 }
 
+// N independent exponentials evaluated in lock step (explicit instruction-level
+// parallelism for warps that cannot rely on occupancy): same reduction and polynomial as
+// exp_sm.  CHECK=false assumes 0 <= t < 700 (results are normal numbers); CHECK=true
+// additionally flushes results below 2^-1021 -- and any argument the magic-constant
+// reduction cannot represent, i.e. t <= -2^27 -- to zero; arguments must not exceed +700.
+template <int N, bool CHECK>
+__device__ __forceinline__ void exp_batch(double (&t)[N]) {
+    const double kMagic = 6755399441055744.0;
+    double sft[N], r[N], p[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) sft[u] = fma(t[u], 1.4426950408889634, kMagic);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const double fn = sft[u] - kMagic;
+        r[u] = fma(fn, -6.93147180559945286e-01, t[u]);
+        r[u] = fma(fn, -2.31904681384629956e-17, r[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(2.50521083854417188e-08, r[u], 2.75573192239858907e-07);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 2.75573192239858907e-06);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 2.48015873015873016e-05);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 1.98412698412698413e-04);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 1.38888888888888894e-03);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 8.33333333333333322e-03);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 4.16666666666666644e-02);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 1.66666666666666657e-01);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 0.5);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const int n = __double2loint(sft[u]);
+        int hi = __double2hiint(p[u]) + n * 1048576;
+        int lo = __double2loint(p[u]);
+        if (CHECK) {
+            // the reduction is valid while sft stays within 2^31 of the magic constant
+            const bool valid = (unsigned)(__double2hiint(sft[u]) - 0x4337ffff) <= 1u;
+            const bool zero = !valid || n < -1021;
+            hi = zero ? 0 : hi;
+            lo = zero ? 0 : lo;
+        }
+        t[u] = __hiloint2double(hi, lo);
+    }
+}
+
 template <int D, int TK, int TF>
 struct Cfg {
     static constexpr int F = n_stat_features(D);

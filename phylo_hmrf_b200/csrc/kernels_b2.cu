@@ -32,6 +32,20 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// producers are not latency critical: back off between polls so the spin does not eat the
+// issue slots of the consumer on the same sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try(bar, parity)) __nanosleep(200);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -103,24 +117,29 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                     if (lane < W) prefetch_l2(a.nbr_id + lane * ld + i2);
                 }
             }
-            const int li = a.labels[a.own_offset + i];
-            const double lp_li = a.logp[li * ld + i];
-
-            // ---- neighbour fold in registers (both half-lanes redundantly)
+            // ---- loads first: neighbour ids and own label, then what depends on them
             int lab[kFastSlots];
             double sw[kFastSlots];
             bool live[kFastSlots];
+            int li;
+            double lp_li;
             {
                 int jid[kFastSlots];
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) jid[s] = s < W ? a.nbr_id[s * ld + i] : -1;
-#pragma unroll
-                for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1 - s;
+                li = a.labels[a.own_offset + i];
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) {
                     sw[s] = 0.0;
-                    if (jid[s] >= 0) sw[s] = weighted ? beta * a.nbr_w[s * ld + i] : beta;
+                    if (s < W && weighted) sw[s] = a.nbr_w[s * ld + i];
+                }
+#pragma unroll
+                for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1 - s;
+                lp_li = a.logp[li * ld + i];
+#pragma unroll
+                for (int s = 0; s < kFastSlots; ++s) {
                     live[s] = jid[s] >= 0;
+                    sw[s] = live[s] ? (weighted ? beta * sw[s] : beta) : 0.0;
                 }
             }
             double pc = 0.0;
@@ -135,6 +154,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                 sw[0] = beta;
                 live[0] = true;
             }
+            // fold duplicate labels into their first occurrence
 #pragma unroll
             for (int s = 1; s < kFastSlots; ++s)
 #pragma unroll
@@ -143,34 +163,32 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                     sw[q] += dup ? sw[s] : 0.0;
                     live[s] = live[s] && !dup;
                 }
-            double s_li = 0.0, fsum = 0.0, f_li = 1.0;
+            double s_li = 0.0;
+#pragma unroll
+            for (int s = 0; s < kFastSlots; ++s) s_li = (live[s] && lab[s] == li) ? sw[s] : s_li;
+            // f_c = exp(S_c) for the (<= 8) distinct neighbour labels, in lock step; the host
+            // only selects this kernel when beta * W * max|w| < 700, so no range checks
+            exp_batch<kFastSlots, false>(sw);
+            double fsum = 0.0, f_li = 1.0;
             int m = 0;
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                if (__any_sync(0xffffffffu, live[s])) {
-                    const double ex = exp_sm(sw[s]);
-                    if (live[s]) {
-                        fsum += ex;
-                        ++m;
-                        if (lab[s] == li) {
-                            s_li = sw[s];
-                            f_li = ex;
-                        }
-                        sw[s] = ex;  // from here on sw holds f_c = exp(S_c)
-                    }
-                }
+                fsum += live[s] ? sw[s] : 0.0;
+                m += live[s] ? 1 : 0;
+                f_li = (live[s] && lab[s] == li) ? sw[s] : f_li;
             }
+            // soft-max of -pp at the node's own label: exp(S_li) / (sum_c exp(S_c) + (K - m))
             const double pwn_log = log(f_li / (fsum + (double)(K - m)) + 1e-16);
 
-            // ---- soft-max terms: shift = max(logp_li + S_li, max_k logp_k - 600)
-            // this lane's share of the log-likelihood row
+            // ---- soft-max terms: shift = max(logp_li + S_li, max_k logp_k - 600); this lane's
+            // share of the log-likelihood row stays in registers
             double e[KTH][TK];
 #pragma unroll
             for (int q = 0; q < KTH; ++q)
 #pragma unroll
                 for (int ii = 0; ii < TK; ++ii) {
                     const int k = (hs * KTH + q) * TK + ii;
-                    e[q][ii] = k < K ? a.logp[k * ld + i] : -INFINITY;
+                    e[q][ii] = k < K ? a.logp[k * ld + i] : -1.0e6;
                 }
             double lpmax = -INFINITY;
 #pragma unroll
@@ -181,16 +199,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
             const double shift = fmax(lp_li + s_li, lpmax - 600.0);
             double esum = 0.0;
 #pragma unroll
-            for (int q = 0; q < KTH; ++q)
+            for (int q = 0; q < KTH; ++q) {
 #pragma unroll
-                for (int ii = 0; ii < TK; ++ii) {
-                    e[q][ii] = exp_sm(e[q][ii] - shift);
-                    esum += e[q][ii];
-                }
+                for (int ii = 0; ii < TK; ++ii) e[q][ii] -= shift;
+                exp_batch<TK, true>(e[q]);
+#pragma unroll
+                for (int ii = 0; ii < TK; ++ii) esum += e[q][ii];
+            }
             esum += __shfl_xor_sync(0xffffffffu, esum, 16);
 
             // ---- slot: wait until the consumer released it, then write the e row
-            if (j > 0) mbar_wait(empty + p, (uint32_t)((j - 1) & 1));
+            if (j > 0) mbar_wait_relaxed(empty + p, (uint32_t)((j - 1) & 1));
 #pragma unroll
             for (int q = 0; q < KTH; ++q) {
                 const int ktile = hs * KTH + q;
@@ -401,6 +420,7 @@ int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handle
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     *handled = false;
     if (!a.potts || a.W > kFastSlots || a.pp_soa != nullptr || a.n == 0) return PHMRF_OK;
+    if (!(a.s_bound < 700.0)) return PHMRF_OK;  // exp(S) must stay finite without range checks
     switch (a.D) {
 #define PHMRF_CASE(DD) \
     case DD:           \

@@ -52,7 +52,8 @@ for r, ln in zip(body, lines):
     a[3] += int(r[ex] or 0)
     a[4] += 1
 srcfile = {}
-for (ln, a) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+sortkey = 1 if len(sys.argv) > 6 and sys.argv[6] == "exec" else 0
+for (ln, a) in sorted(agg.items(), key=lambda kv: -kv[1][sortkey])[:top]:
     text = ""
     if ln:
         try:
