@@ -103,152 +103,167 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
         double c_pair = 0.0, c_pwn = 0.0, c_un = 0.0;
         int bad_any = 0;
         int64_t j = 0;
+        // lane-constant offsets of this half-lane's first state
+        const int k_first = hs * KTH * TK;
+        const int split = KTH * TK;  // states >= split belong to the upper half-lane
         for (int64_t T = (int64_t)blockIdx.x * kProducers + p; T < n_tiles; T += tile_stride_g, ++j) {
             const int64_t i_raw = T * kTileNodes + nd;
             const bool valid = i_raw < n;
             const int64_t i = valid ? i_raw : n - 1;
-            {   // pull this producer's next tile towards L2
+            {   // pull this producer's next tile towards L2 (one 128-byte line per row and tile)
                 const int64_t T2 = T + tile_stride_g;
                 if (T2 < n_tiles) {
                     const int64_t i2 = T2 * kTileNodes;
-                    for (int q = lane; q < K; q += 32) prefetch_l2(a.logp + q * ld + i2);
+                    const double *row = a.logp + lane * ld + i2;
+                    if (lane < K) prefetch_l2(row);
+                    if (lane + 32 < K) prefetch_l2(row + 32 * ld);
                     if (lane < D) prefetch_l2(a.X_soa + lane * ld + i2);
                     if (lane < W) prefetch_l2(a.nbr_w + lane * ld + i2);
                     if (lane < W) prefetch_l2(a.nbr_id + lane * ld + i2);
                 }
             }
-            // ---- loads first: neighbour ids and own label, then what depends on them
+            // ---- loads first: neighbour ids and own label, then what depends on them.
             int lab[kFastSlots];
             double sw[kFastSlots];
-            bool live[kFastSlots];
             int li;
             double lp_li;
             {
                 int jid[kFastSlots];
+                const int32_t *pid = a.nbr_id + i;
 #pragma unroll
-                for (int s = 0; s < kFastSlots; ++s) jid[s] = s < W ? a.nbr_id[s * ld + i] : -1;
+                for (int s = 0; s < kFastSlots; ++s) {
+                    jid[s] = s < W ? *pid : -1;
+                    pid += ld;
+                }
                 li = a.labels[a.own_offset + i];
+                const double *pw = a.nbr_w + i;
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) {
-                    sw[s] = 0.0;
-                    if (s < W && weighted) sw[s] = a.nbr_w[s * ld + i];
+                    sw[s] = (s < W && weighted) ? *pw : 1.0;
+                    pw += ld;
                 }
 #pragma unroll
-                for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1 - s;
+                for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1;
                 lp_li = a.logp[li * ld + i];
-#pragma unroll
-                for (int s = 0; s < kFastSlots; ++s) {
-                    live[s] = jid[s] >= 0;
-                    sw[s] = live[s] ? (weighted ? beta * sw[s] : beta) : 0.0;
-                }
             }
-            double pc = 0.0;
-            bool any_nbr = false;
+            // this lane's share of the log-likelihood row (registers; issued before the
+            // neighbour arithmetic so that its latency overlaps)
+            double e[KTH][TK];
+            {
+                const double *pk = a.logp + (int64_t)k_first * ld + i;
+#pragma unroll
+                for (int q = 0; q < KTH; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < TK; ++ii) {
+                        const int k = k_first + q * TK + ii;
+                        e[q][ii] = k < K ? *pk : -1.0e6;
+                        pk += ld;
+                    }
+            }
+            int all_neg = -1;  // sign bit stays set while no slot holds a neighbour
+            double pc = 0.0;   // sum over the incident edges of V[l_nbr, l_i] * w
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                any_nbr |= live[s];
-                pc += (live[s] && lab[s] != li) ? sw[s] : 0.0;
+                sw[s] = lab[s] >= 0 ? beta * sw[s] : 0.0;
+                all_neg &= lab[s];
+                pc += lab[s] != li ? sw[s] : 0.0;  // an empty slot has weight 0
             }
-            if (!any_nbr) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
+            if (all_neg < 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
                 lab[0] = li;
                 sw[0] = beta;
-                live[0] = true;
             }
-            // fold duplicate labels into their first occurrence
-#pragma unroll
-            for (int s = 1; s < kFastSlots; ++s)
-#pragma unroll
-                for (int q = 0; q < s; ++q) {
-                    const bool dup = live[s] && live[q] && lab[q] == lab[s];
-                    sw[q] += dup ? sw[s] : 0.0;
-                    live[s] = live[s] && !dup;
-                }
-            double s_li = 0.0;
-#pragma unroll
-            for (int s = 0; s < kFastSlots; ++s) s_li = (live[s] && lab[s] == li) ? sw[s] : s_li;
-            // f_c = exp(S_c) for the (<= 8) distinct neighbour labels, in lock step; the host
-            // only selects this kernel when beta * W * max|w| < 700, so no range checks
+            // g_s = exp(beta*w_s) per slot, in lock step.  The host only selects this kernel when
+            // beta * W * max|w| < 100, so no range checks.  (A slot without neighbour gives 1.)
             exp_batch<kFastSlots, false>(sw);
-            double fsum = 0.0, f_li = 1.0;
-            int m = 0;
-#pragma unroll
-            for (int s = 0; s < kFastSlots; ++s) {
-                fsum += live[s] ? sw[s] : 0.0;
-                m += live[s] ? 1 : 0;
-                f_li = (live[s] && lab[s] == li) ? sw[s] : f_li;
-            }
-            // soft-max of -pp at the node's own label: exp(S_li) / (sum_c exp(S_c) + (K - m))
-            const double pwn_log = log(f_li / (fsum + (double)(K - m)) + 1e-16);
 
-            // ---- soft-max terms: shift = max(logp_li + S_li, max_k logp_k - 600); this lane's
-            // share of the log-likelihood row stays in registers
-            double e[KTH][TK];
+            // ---- soft-max shift = max(logp_li, ~max_k logp_k - 600).  The maximum only has to be
+            // right to about one unit, so it is taken on the order-preserving integer image of the
+            // high words (3 integer instructions per value instead of an FP64 compare/select).
+            int kmax = (int)0x80000000;
 #pragma unroll
             for (int q = 0; q < KTH; ++q)
 #pragma unroll
                 for (int ii = 0; ii < TK; ++ii) {
-                    const int k = (hs * KTH + q) * TK + ii;
-                    e[q][ii] = k < K ? a.logp[k * ld + i] : -1.0e6;
+                    const int h = __double2hiint(e[q][ii]);
+                    kmax = max(kmax, h ^ ((h >> 31) & 0x7fffffff));
                 }
-            double lpmax = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < KTH; ++q)
-#pragma unroll
-                for (int ii = 0; ii < TK; ++ii) lpmax = fmax(lpmax, e[q][ii]);
-            lpmax = fmax(lpmax, __shfl_xor_sync(0xffffffffu, lpmax, 16));
-            const double shift = fmax(lp_li + s_li, lpmax - 600.0);
-            double esum = 0.0;
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, 16));
+            const double lpmax = __hiloint2double(kmax ^ ((kmax >> 31) & 0x7fffffff), 0);
+            const double shift = fmax(lp_li, lpmax - 598.0);
 #pragma unroll
             for (int q = 0; q < KTH; ++q) {
 #pragma unroll
                 for (int ii = 0; ii < TK; ++ii) e[q][ii] -= shift;
                 exp_batch<TK, true>(e[q]);
-#pragma unroll
-                for (int ii = 0; ii < TK; ++ii) esum += e[q][ii];
             }
-            esum += __shfl_xor_sync(0xffffffffu, esum, 16);
 
-            // ---- slot: wait until the consumer released it, then write the e row
+            // ---- slot: wait until the consumer released it.  The P row first holds
+            // G_k = exp(S_k), S_k = sum of beta*w over the neighbours labelled k, built by
+            // multiplying g_s into G[label_s] slot by slot (no duplicate-label bookkeeping:
+            // exp(a)exp(b) = exp(a+b)); each half-lane owns the states of its own half.
             if (j > 0) mbar_wait_relaxed(empty + p, (uint32_t)((j - 1) & 1));
 #pragma unroll
             for (int q = 0; q < KTH; ++q) {
                 const int ktile = hs * KTH + q;
                 if (ktile < nkt_total) {
-                    double ev[even_up(TK)];
-#pragma unroll
-                    for (int ii = 0; ii < even_up(TK); ++ii) ev[ii] = ii < TK ? e[q][ii] : 0.0;
 #pragma unroll
                     for (int c = 0; c < even_up(TK); c += 2)
-                        *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(ev[c], ev[c + 1]);
+                        *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(1.0, 1.0);
                 }
             }
-            __syncwarp();
-            // patch the <= 8 distinct neighbour labels: e_c *= exp(S_c); slots split between the lanes
-            double de = 0.0;
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                if (__any_sync(0xffffffffu, live[s])) {
-                    if (live[s] && (s & 1) == hs) {
-                        const int pos = (lab[s] / TK) * TKs + (lab[s] % TK);
-                        const double e_old = Prow[pos];
-                        const double e_new = e_old * sw[s];
-                        Prow[pos] = e_new;
-                        de += e_new - e_old;
-                    }
+                if (lab[s] >= 0 && (lab[s] >= split) == (hs != 0)) {
+                    const int kt_s = lab[s] / TK;
+                    double *g = Prow + kt_s * (TKs - TK) + lab[s];
+                    *g = *g * sw[s];
                 }
             }
-            de += __shfl_xor_sync(0xffffffffu, de, 16);
-            esum += de;
-            const bool bad = !(esum <= DBL_MAX) || !(fsum <= DBL_MAX) || !(esum > 0.0);
+            // e_k = exp(logp_k - shift) * G_k, written over G; Q = sum_k G_k on the way
+            double esum = 0.0, qsum = 0.0, g_li = 0.0;
+#pragma unroll
+            for (int q = 0; q < KTH; ++q) {
+                const int ktile = hs * KTH + q;
+                if (ktile < nkt_total) {
+                    double g[even_up(TK)];
+#pragma unroll
+                    for (int c = 0; c < even_up(TK); c += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(Prow + ktile * TKs + c);
+                        g[c] = v.x;
+                        g[c + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < TK; ++ii) {
+                        const int k = ktile * TK + ii;
+                        if (k < K) qsum += g[ii];
+                        g_li = k == li ? g[ii] : g_li;
+                        g[ii] *= e[q][ii];
+                        esum += g[ii];
+                    }
+                    if (TK < even_up(TK)) g[even_up(TK) - 1] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < even_up(TK); c += 2)
+                        *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(g[c], g[c + 1]);
+                }
+            }
+            esum += __shfl_xor_sync(0xffffffffu, esum, 16);
+            qsum += __shfl_xor_sync(0xffffffffu, qsum, 16);
+            g_li += __shfl_xor_sync(0xffffffffu, g_li, 16);
+            // soft-max of -pp at the node's own label: exp(S_li) / sum_k exp(S_k)
+            const double pwn_log = log(g_li / qsum + 1e-16);
+            const bool bad = !(esum <= DBL_MAX) || !(qsum <= DBL_MAX) || !(esum > 0.0);
             bad_any |= bad ? 1 : 0;
             const double inv = valid ? 1.0 / esum : 0.0;
             {
                 double x[D], xs[D];
+                const double *px = a.X_soa + i;
 #pragma unroll
                 for (int jx = 0; jx < D; ++jx) {
-                    x[jx] = a.X_soa[jx * ld + i];
-                    xs[jx] = x[jx] * inv;
+                    x[jx] = *px;
+                    px += ld;
                 }
+#pragma unroll
+                for (int jx = 0; jx < D; ++jx) xs[jx] = x[jx] * inv;
                 constexpr int NCH = RSY / 2, H0 = NCH / 2;
                 if (hs == 0)
                     write_y_chunks<D, TF, TFs, 0>(Yrow, x, xs, inv, std::make_integer_sequence<int, H0>{});
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                     write_y_chunks<D, TF, TFs, H0>(Yrow, x, xs, inv, std::make_integer_sequence<int, NCH - H0>{});
             }
             if (valid && hs == 0) {
-                c_pair += pc;
+                c_pair += all_neg < 0 ? 0.0 : pc;
                 c_un += lp_li;
                 c_pwn += pwn_log;
             }
@@ -420,7 +435,7 @@ int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handle
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     *handled = false;
     if (!a.potts || a.W > kFastSlots || a.pp_soa != nullptr || a.n == 0) return PHMRF_OK;
-    if (!(a.s_bound < 700.0)) return PHMRF_OK;  // exp(S) must stay finite without range checks
+    if (!(a.s_bound < 100.0)) return PHMRF_OK;  // exp(S) * exp(600) must stay finite without range checks
     switch (a.D) {
 #define PHMRF_CASE(DD) \
     case DD:           \
