@@ -303,3 +303,33 @@ def test_native_library_is_the_one_loaded(ph):
     assert "phylo_hmrf_b200/lib/libphmrf.so" in maps
     from phylo_hmrf_b200 import engine
     assert engine.launch_count() > 0
+
+
+def test_quantiser_division_is_correctly_rounded(ph):
+    """The integer unary must equal numpy's ((u / dwf) * 1e5).astype(intc) bit for bit on
+    identical inputs: exercise the refinement-based division with adversarial magnitudes and
+    many different down-weight factors (injected log-likelihoods, dwf override)."""
+    rng = np.random.default_rng(123)
+    K, d, n = 16, 2, 4096
+    m = ph.Model(K, d)
+    m.set_model(np.zeros((K, d)), np.stack([np.eye(d)] * K), np.zeros((K, K)))
+    reg = m.region(np.zeros((n, d)), np.zeros((0, 2), np.int64), np.zeros(0))
+    for trial in range(12):
+        mag = 10.0 ** rng.uniform(-3, 6, size=(n, K))
+        lp = -mag * rng.uniform(0.5, 1.0, size=(n, K)) * np.where(rng.random((n, K)) < 0.1, -1.0, 1.0)
+        if trial % 3 == 0:  # values sitting on / next to truncation boundaries
+            dwf = float(np.abs(lp).max() * rng.uniform(1.0, 1.5))
+            ints = rng.integers(-99999, 99999, size=(n, K))
+            lp = -(ints / 1e5) * dwf
+            lp = np.nextafter(lp, np.where(rng.random((n, K)) < 0.5, np.inf, -np.inf))
+        else:
+            dwf = float(np.abs(lp).max() * rng.uniform(1.0, 3.0) + 1e-10)
+        reg.set_logprob(lp)
+        q = reg.quantise(dwf=dwf, want_edges=False, boundary_cap=n * K)
+        ref = ((-lp / dwf) * 100000).astype(np.intc)
+        assert q["dwf"] == dwf
+        assert np.array_equal(q["unary_i32"], ref)
+        mask = orc.unary_boundary_mask(-lp, dwf, 1e-9).ravel()
+        assert set(np.flatnonzero(mask).tolist()) == set(q["boundary_idx"].tolist())
+    reg.close()
+    m.close()
