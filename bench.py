@@ -170,14 +170,17 @@ def run_ours(args):
 
     stats_len = m.stats_len
 
-    class _Wrap:  # expose the library's device statistics buffer to torch (for NCCL)
-        def __init__(self, ptr, nelem):
-            self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-    stats_dev = torch.as_tensor(_Wrap(reg.stats_device_ptr(), stats_len), device="cuda")
+    from phylo_hmrf_b200 import dist as pdist
+    stats_dev = pdist.stats_tensor(reg)      # the library's device statistics buffer (for NCCL)
+    absmax_dev = pdist.absmax_tensor(reg)    # max|logp| of the band as ordered int64 bits
+    if world > 1:
+        pdist.share_weight_max(reg, dist)    # the bands are ONE region: shared down-weight factor
 
     def step():
         reg.emit_loglik_async()
+        if world > 1:                        # region-wide max|logp| before the integer conversion
+            with torch.cuda.stream(stream):
+                dist.all_reduce(absmax_dev, op=dist.ReduceOp.MAX)
         ev[1].record(stream)
         reg.quantise_async()
         ev[2].record(stream)

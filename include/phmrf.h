@@ -136,6 +136,14 @@ int phmrf_estep_stats(phmrf_region *r, int estimate_type, double *post_out, doub
  * point exists for signature parity and for tests. */
 int phmrf_pairwise_potential(phmrf_region *r, int estimate_type, double *pp_out);
 void *phmrf_stats_device_ptr(phmrf_region *r);
+/* Row bands of ONE region spread over several GPUs must share pygco's down_weight_factor.
+ * phmrf_absmax_device_ptr: device address of max|logp| of this band, stored as the uint64 bit
+ * pattern of a non-negative double (integer order == numeric order), ready for an NCCL
+ * max-all-reduce between phmrf_emit_loglik_async and phmrf_quantise_async.
+ * phmrf_region_set_weight_max: replace the band-local max|w| by the region-wide one. */
+void *phmrf_absmax_device_ptr(phmrf_region *r);
+int phmrf_region_set_weight_max(phmrf_region *r, double wmax);
+double phmrf_region_weight_max(const phmrf_region *r);
 int64_t phmrf_stats_len(const phmrf_ctx *ctx);
 
 /* Enqueue-only forms used by the bench (no host copies, no synchronisation). */

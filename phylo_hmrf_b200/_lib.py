@@ -53,6 +53,9 @@ SIGNATURES = {
     "phmrf_estep_stats": (C.c_int, [_vp, C.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "phmrf_stats_device_ptr": (_vp, [_vp]),
     "phmrf_stats_len": (C.c_int64, [_vp]),
+    "phmrf_absmax_device_ptr": (_vp, [_vp]),
+    "phmrf_region_set_weight_max": (C.c_int, [_vp, C.c_double]),
+    "phmrf_region_weight_max": (C.c_double, [_vp]),
     "phmrf_emit_loglik_async": (C.c_int, [_vp]),
     "phmrf_quantise_async": (C.c_int, [_vp, C.c_double, C.c_double]),
     "phmrf_estep_stats_async": (C.c_int, [_vp, C.c_int]),

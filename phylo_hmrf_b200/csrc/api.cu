@@ -412,6 +412,13 @@ int64_t phmrf_stats_len(const phmrf_ctx *ctx) {
 }
 
 void *phmrf_stats_device_ptr(phmrf_region *r) { return r ? (void *)r->d_stats : nullptr; }
+void *phmrf_absmax_device_ptr(phmrf_region *r) { return r ? (void *)r->d_absmax : nullptr; }
+double phmrf_region_weight_max(const phmrf_region *r) { return r ? r->wmax : 0.0; }
+int phmrf_region_set_weight_max(phmrf_region *r, double wmax) {
+    if (!r || !(wmax >= 0.0)) return PHMRF_E_INVALID;
+    r->wmax = wmax;
+    return PHMRF_OK;
+}
 
 // ---------------------------------------------------------------- phase A
 int phmrf_emit_loglik_async(phmrf_region *r) {

@@ -154,6 +154,15 @@ class Region:
     def sync(self):
         check(_lib.lib().phmrf_region_sync(self._h))
 
+    def absmax_device_ptr(self):
+        return int(_lib.lib().phmrf_absmax_device_ptr(self._h))
+
+    def weight_max(self):
+        return float(_lib.lib().phmrf_region_weight_max(self._h))
+
+    def set_weight_max(self, wmax):
+        check(_lib.lib().phmrf_region_set_weight_max(self._h, float(wmax)))
+
     def stats_device_ptr(self):
         return int(_lib.lib().phmrf_stats_device_ptr(self._h))
 

@@ -1,0 +1,94 @@
+"""World-size-2 (gloo, CPU) test of the multi-GPU host logic: row-band sharding with halo,
+the shared down-weight factor, and the all-reduce of statistics / cost sums.  The per-band
+arithmetic is the CPU oracle here (no GPU in this tier); the same glue drives the CUDA path
+in bench.py and tests/test_gpu_parity.py::test_row_bands_add_up_to_the_whole_region."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import phmrf_oracle as orc
+from phylo_hmrf_b200 import synth
+from phylo_hmrf_b200 import dist as pdist
+
+B, D, K, ET, SEED = 40, 4, 6, 3, 31
+
+
+def _band_oracle(g, means, covars, V, labels_window, dwf=None):
+    """What one rank computes for its band (oracle stand-in for the kernels)."""
+    o0, n = g["own_offset"], g["n_own"]
+    X = g["X_own"]
+    lp = orc.compute_log_likelihood(X, means, covars)
+    # window-sized arrays so that the vectorised oracle sees the halo labels; rows outside the
+    # band are zero-filled and excluded from the sums below
+    lp_win = np.zeros((g["n_window"], K))
+    lp_win[o0:o0 + n] = lp
+    pp = orc.pairwise_compare_vec(V, labels_window, g["edge_w"], g["edge_ids"], ET)[o0:o0 + n]
+    lab = labels_window[o0:o0 + n]
+    post = orc._stable_softmax(lp - pp)
+    pwn = orc._stable_softmax(-pp)
+    st = orc.sufficient_statistics(post, X)
+    e = g["edge_ids"]
+    la, lb = labels_window[e[:, 0]], labels_window[e[:, 1]]
+    per_node = np.zeros(g["n_window"])
+    np.add.at(per_node, e[:, 1], V[la, lb] * g["edge_w"])
+    np.add.at(per_node, e[:, 0], V[lb, la] * g["edge_w"])
+    sums = np.array([per_node[o0:o0 + n].sum(), np.log(pwn[np.arange(n), lab] + 1e-16).sum(),
+                     lp[np.arange(n), lab].sum()])
+    flat = np.concatenate([st["post"], st["obs"].ravel(), st["obs*obs.T"].ravel()])
+    return lp, flat, sums
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        whole = synth.make_band(SEED, B, D)
+        means, covars = synth.model(SEED, whole["X_own"], K, D)
+        V = synth.potts(K, 1.0)
+        r0, r1 = synth.band_rows(B, world)[rank]
+        g = synth.make_band(SEED, B, D, r0, r1)
+        lp = orc.compute_log_likelihood(g["X_own"], means, covars)
+        dwf = pdist.global_dwf(np.abs(lp).max(), np.abs(g["edge_w"]).max(), V.max(), dist)
+        u_band = ((-lp / dwf) * 100000).astype(np.intc)
+        # labels of the whole region: arg-min unary gathered from all bands (stand-in for GCO)
+        parts = [None] * world
+        dist.all_gather_object(parts, (g["win_start"] + g["own_offset"], np.argmin(u_band, axis=1)))
+        labels = np.zeros(whole["n_own"], dtype=np.int64)
+        for off, lab in parts:
+            labels[off:off + len(lab)] = lab
+        lab_win = labels[g["win_start"]:g["win_start"] + g["n_window"]]
+        _, flat, sums = _band_oracle(g, means, covars, V, lab_win)
+        stats, costs, n_total = pdist.combine_band_results(flat, sums, g["n_own"], dist)
+        if rank == 0:
+            np.savez(out, dwf=dwf, stats=stats, costs=np.asarray(costs), n_total=n_total, labels=labels)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_band_sharding_matches_single_region(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "rank0.npz")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    whole = synth.make_band(SEED, B, D)
+    means, covars = synth.model(SEED, whole["X_own"], K, D)
+    V = synth.potts(K, 1.0)
+    lp = orc.compute_log_likelihood(whole["X_own"], means, covars)
+    u, _, _, dwf = orc.pygco_quantise(-lp, whole["edge_w"], V)
+    assert got["dwf"] == dwf
+    labels = np.argmin(u, axis=1)
+    assert np.array_equal(got["labels"], labels)
+    ref = orc.compute_posteriors_graph(V, labels, lp, whole["edge_w"], whole["edge_ids"], None, ET, faithful=False,
+                                       stable=True)
+    st = orc.sufficient_statistics(ref[0], whole["X_own"])
+    flat = np.concatenate([st["post"], st["obs"].ravel(), st["obs*obs.T"].ravel()])
+    assert int(got["n_total"]) == whole["n_own"]
+    np.testing.assert_allclose(got["stats"], flat, rtol=1e-12)
+    np.testing.assert_allclose(got["costs"], ref[1:], rtol=1e-12)
