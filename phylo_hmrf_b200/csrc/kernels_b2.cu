@@ -1,16 +1,21 @@
 // Phase B, warp-specialised pipeline (the fast path for the reference's own model shape:
-// Potts compatibility, <= 8 neighbour slots, K within one register-tile pass).
+// Potts compatibility, <= 8 neighbour slots, K <= 40 states).
 //
 // One CTA per SM, 16 warps:
-//   warps 0-3   CONSUMERS (one per SM sub-partition, 232 registers): hold the K x F
-//               sufficient-statistic accumulators as TK x TF register tiles and do nothing
-//               but  S[k][f] += e[n][k] * y[n][f]  from shared-memory rows (LDS.128 + DFMA).
-//   warps 4-15  PRODUCERS (88 registers): the latency-bound per-node work -- neighbour
-//               gather, duplicate-label fold, soft-max terms, cost scalars, feature row --
-//               for tiles of 16 nodes, two lanes per node (each lane takes half the states).
+//   warps 0-3   CONSUMERS (one per SM sub-partition): hold the K x F sufficient-statistic
+//               accumulators and do nothing but  S[k][f] += e[n][k] * y[n][f].  This is a
+//               dense (K x n)(n x F) FP64 product, issued as DMMA.8x8x4 (mma.sync m8n8k4
+//               f64): on B200 the FP64 mma shares the DFMA datapath (same measured peak,
+//               36.6-37.1 TFLOP/s), but one instruction carries 256 FMAs and takes ONE
+//               operand per lane, so the stat phase needs 8x fewer issue slots and 4.5x fewer
+//               shared-memory wavefronts than the DFMA formulation it replaced (ncu: LSU
+//               wavefronts were at 72 % of peak and the sub-partition issue port was the
+//               limiter, see profiles/r1_history.md).
+//   warps 4-15  PRODUCERS: the latency-bound per-node work -- neighbour gather, soft-max
+//               terms, cost scalars, feature row -- for tiles of 16 nodes, two lanes per node
+//               (each lane takes half the states).
 // A producer owns one shared-memory slot (16 P rows + 16 Y rows); producer p feeds consumer
-// p % 4 through a full/empty mbarrier pair, so the FP64 pipe of every sub-partition always
-// has the consumer's independent DFMA stream to issue while producers wait on memory.
+// p % 4 through a full/empty mbarrier pair.
 // Same arithmetic as kernels_b.cu (reference: phylo_hmrf.py:311-314, 334-468).
 #include "estep_common.cuh"
 
@@ -32,19 +37,17 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// producers are not latency critical: back off between polls so the spin does not eat the
-// issue slots of the consumer on the same sub-partition
+// producers are not latency critical: let the hardware suspend the warp on the barrier
+// instead of spinning next to the consumer that shares its sub-partition
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try(bar, parity)) __nanosleep(200);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -57,22 +60,49 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-template <int D, int TF, int TFs, int C0, int... Cs>
-__device__ __forceinline__ void write_y_chunks(double *Yrow, const double (&x)[D], const double (&xs)[D], double inv,
-                                               std::integer_sequence<int, Cs...>) {
+// D(8x8) += A(8x4) * B(4x8), FP64.  Lane (g = lane/4, t = lane%4) supplies A[g][t], B[t][g]
+// and holds D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// dense feature row: position f holds feature f (1, x, x (x) x packed), zero beyond F
+template <int D, int POS>
+__device__ __forceinline__ double yd_at(const double (&x)[D], const double (&xs)[D], double inv) {
+    constexpr int F = n_stat_features(D);
+    if constexpr (POS >= F) {
+        return 0.0;
+    } else if constexpr (POS == 0) {
+        return inv;
+    } else if constexpr (POS <= D) {
+        return xs[POS - 1];
+    } else {
+        constexpr int r = POS - 1 - D;
+        return xs[tri_row_of(r, D)] * x[tri_col_of(r, D)];
+    }
+}
+template <int D, int C0, int... Cs>
+__device__ __forceinline__ void write_yd_chunks(double *Yrow, const double (&x)[D], const double (&xs)[D], double inv,
+                                                std::integer_sequence<int, Cs...>) {
     ((*reinterpret_cast<double2 *>(Yrow + 2 * (C0 + Cs)) =
-          make_double2(y_at<D, TF, TFs, 2 * (C0 + Cs)>(x, xs, inv), y_at<D, TF, TFs, 2 * (C0 + Cs) + 1>(x, xs, inv))),
+          make_double2(yd_at<D, 2 * (C0 + Cs)>(x, xs, inv), yd_at<D, 2 * (C0 + Cs) + 1>(x, xs, inv))),
      ...);
 }
 
-template <int D, int TK, int TF, int KTH>
-__global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a, int nkt_total, int rsp) {
-    using C = Cfg<D, TK, TF>;
-    constexpr int F = C::F, TKs = C::TKs, TFs = C::TFs, NFT = C::NFT, RSY = C::RSY;
-    // KTH = k tiles per half-lane of a producer (template: sizes the register row)
+// NK8 = number of 8-state tiles (K <= 8*NK8); each producer half-lane owns KH = 4*NK8 states.
+template <int D, int NK8>
+__global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a) {
+    constexpr int F = n_stat_features(D);
+    constexpr int NT = (F + 7) / 8;        // 8-feature tiles
+    constexpr int KP = 8 * NK8, FP = 8 * NT;
+    constexpr int RSP = KP + 4, RSY = FP + 4;  // == 4 (mod 8): the DMMA operand loads are conflict free
+    constexpr int KH = KP / 2;
+    constexpr int EB = 4;                   // exponentials evaluated in lock step
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot_doubles = kTileNodes * (rsp + RSY);
+    constexpr int slot_doubles = kTileNodes * (RSP + RSY);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kProducers * slot_doubles);
     uint64_t *full = bars, *empty = bars + kProducers;
     if (threadIdx.x == 0) {
@@ -92,20 +122,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
 
     if (warp >= kConsumers) {
         // =============================== PRODUCER ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
         const int p = warp - kConsumers;
         double *slot = smem + (size_t)p * slot_doubles;
         const int nd = lane & 15, hs = lane >> 4;
-        double *Prow = slot + nd * rsp;
-        double *Yrow = slot + kTileNodes * rsp + nd * RSY;
+        double *Prow = slot + nd * RSP;
+        double *Yrow = slot + kTileNodes * RSP + nd * RSY;
         const bool weighted = a.estimate_type == 3;
         const double beta = a.beta;
+        const int k_first = hs * KH;
         double c_pair = 0.0, c_pwn = 0.0, c_un = 0.0;
         int bad_any = 0;
         int64_t j = 0;
-        // lane-constant offsets of this half-lane's first state
-        const int k_first = hs * KTH * TK;
-        const int split = KTH * TK;  // states >= split belong to the upper half-lane
         for (int64_t T = (int64_t)blockIdx.x * kProducers + p; T < n_tiles; T += tile_stride_g, ++j) {
             const int64_t i_raw = T * kTileNodes + nd;
             const bool valid = i_raw < n;
@@ -148,17 +176,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
             }
             // this lane's share of the log-likelihood row (registers; issued before the
             // neighbour arithmetic so that its latency overlaps)
-            double e[KTH][TK];
+            double e[KH];
             {
                 const double *pk = a.logp + (int64_t)k_first * ld + i;
 #pragma unroll
-                for (int q = 0; q < KTH; ++q)
-#pragma unroll
-                    for (int ii = 0; ii < TK; ++ii) {
-                        const int k = k_first + q * TK + ii;
-                        e[q][ii] = k < K ? *pk : -1.0e6;
-                        pk += ld;
-                    }
+                for (int q = 0; q < KH; ++q) {
+                    e[q] = (k_first + q) < K ? *pk : -1.0e6;
+                    pk += ld;
+                }
             }
             int all_neg = -1;  // sign bit stays set while no slot holds a neighbour
             double pc = 0.0;   // sum over the incident edges of V[l_nbr, l_i] * w
@@ -176,25 +201,26 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
             // beta * W * max|w| < 100, so no range checks.  (A slot without neighbour gives 1.)
             exp_batch<kFastSlots, false>(sw);
 
-            // ---- soft-max shift = max(logp_li, ~max_k logp_k - 600).  The maximum only has to be
+            // ---- soft-max shift = max(logp_li, ~max_k logp_k - 598).  The maximum only has to be
             // right to about one unit, so it is taken on the order-preserving integer image of the
             // high words (3 integer instructions per value instead of an FP64 compare/select).
             int kmax = (int)0x80000000;
 #pragma unroll
-            for (int q = 0; q < KTH; ++q)
-#pragma unroll
-                for (int ii = 0; ii < TK; ++ii) {
-                    const int h = __double2hiint(e[q][ii]);
-                    kmax = max(kmax, h ^ ((h >> 31) & 0x7fffffff));
-                }
+            for (int q = 0; q < KH; ++q) {
+                const int h = __double2hiint(e[q]);
+                kmax = max(kmax, h ^ ((h >> 31) & 0x7fffffff));
+            }
             kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, 16));
             const double lpmax = __hiloint2double(kmax ^ ((kmax >> 31) & 0x7fffffff), 0);
             const double shift = fmax(lp_li, lpmax - 598.0);
 #pragma unroll
-            for (int q = 0; q < KTH; ++q) {
+            for (int q0 = 0; q0 < KH; q0 += EB) {
+                double tb[EB];
 #pragma unroll
-                for (int ii = 0; ii < TK; ++ii) e[q][ii] -= shift;
-                exp_batch<TK, true>(e[q]);
+                for (int u = 0; u < EB; ++u) tb[u] = e[q0 + u] - shift;
+                exp_batch<EB, true>(tb);
+#pragma unroll
+                for (int u = 0; u < EB; ++u) e[q0 + u] = tb[u];
             }
 
             // ---- slot: wait until the consumer released it.  The P row first holds
@@ -202,49 +228,26 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
             // multiplying g_s into G[label_s] slot by slot (no duplicate-label bookkeeping:
             // exp(a)exp(b) = exp(a+b)); each half-lane owns the states of its own half.
             if (j > 0) mbar_wait_relaxed(empty + p, (uint32_t)((j - 1) & 1));
+            double *Ph = Prow + k_first;
 #pragma unroll
-            for (int q = 0; q < KTH; ++q) {
-                const int ktile = hs * KTH + q;
-                if (ktile < nkt_total) {
-#pragma unroll
-                    for (int c = 0; c < even_up(TK); c += 2)
-                        *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(1.0, 1.0);
-                }
-            }
+            for (int c = 0; c < KH; c += 2) *reinterpret_cast<double2 *>(Ph + c) = make_double2(1.0, 1.0);
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                if (lab[s] >= 0 && (lab[s] >= split) == (hs != 0)) {
-                    const int kt_s = lab[s] / TK;
-                    double *g = Prow + kt_s * (TKs - TK) + lab[s];
-                    *g = *g * sw[s];
-                }
+                if (lab[s] >= 0 && (lab[s] >= KH) == (hs != 0)) Prow[lab[s]] *= sw[s];
             }
             // e_k = exp(logp_k - shift) * G_k, written over G; Q = sum_k G_k on the way
             double esum = 0.0, qsum = 0.0, g_li = 0.0;
 #pragma unroll
-            for (int q = 0; q < KTH; ++q) {
-                const int ktile = hs * KTH + q;
-                if (ktile < nkt_total) {
-                    double g[even_up(TK)];
-#pragma unroll
-                    for (int c = 0; c < even_up(TK); c += 2) {
-                        const double2 v = *reinterpret_cast<const double2 *>(Prow + ktile * TKs + c);
-                        g[c] = v.x;
-                        g[c + 1] = v.y;
-                    }
-#pragma unroll
-                    for (int ii = 0; ii < TK; ++ii) {
-                        const int k = ktile * TK + ii;
-                        if (k < K) qsum += g[ii];
-                        g_li = k == li ? g[ii] : g_li;
-                        g[ii] *= e[q][ii];
-                        esum += g[ii];
-                    }
-                    if (TK < even_up(TK)) g[even_up(TK) - 1] = 0.0;
-#pragma unroll
-                    for (int c = 0; c < even_up(TK); c += 2)
-                        *reinterpret_cast<double2 *>(Prow + ktile * TKs + c) = make_double2(g[c], g[c + 1]);
-                }
+            for (int c = 0; c < KH; c += 2) {
+                double2 v = *reinterpret_cast<const double2 *>(Ph + c);
+                if (k_first + c < K) qsum += v.x;
+                if (k_first + c + 1 < K) qsum += v.y;
+                g_li = (k_first + c) == li ? v.x : g_li;
+                g_li = (k_first + c + 1) == li ? v.y : g_li;
+                v.x *= e[c];
+                v.y *= e[c + 1];
+                esum += v.x + v.y;
+                *reinterpret_cast<double2 *>(Ph + c) = v;
             }
             esum += __shfl_xor_sync(0xffffffffu, esum, 16);
             qsum += __shfl_xor_sync(0xffffffffu, qsum, 16);
@@ -264,11 +267,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                 }
 #pragma unroll
                 for (int jx = 0; jx < D; ++jx) xs[jx] = x[jx] * inv;
-                constexpr int NCH = RSY / 2, H0 = NCH / 2;
+                constexpr int NCH = FP / 2, H0 = NCH / 2;
                 if (hs == 0)
-                    write_y_chunks<D, TF, TFs, 0>(Yrow, x, xs, inv, std::make_integer_sequence<int, H0>{});
+                    write_yd_chunks<D, 0>(Yrow, x, xs, inv, std::make_integer_sequence<int, H0>{});
                 else
-                    write_y_chunks<D, TF, TFs, H0>(Yrow, x, xs, inv, std::make_integer_sequence<int, NCH - H0>{});
+                    write_yd_chunks<D, H0>(Yrow, x, xs, inv, std::make_integer_sequence<int, NCH - H0>{});
             }
             if (valid && hs == 0) {
                 c_pair += all_neg < 0 ? 0.0 : pc;
@@ -276,23 +279,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                 c_pwn += pwn_log;
             }
             if (a.post_soa != nullptr) {
-                __syncwarp();
                 if (valid) {
 #pragma unroll
-                    for (int q = 0; q < KTH; ++q)
-#pragma unroll
-                        for (int ii = 0; ii < TK; ++ii) {
-                            const int ktile = hs * KTH + q;
-                            const int k = ktile * TK + ii;
-                            if (k < K) a.post_soa[k * ld + i] = Prow[ktile * TKs + ii] * inv;
-                        }
+                    for (int q = 0; q < KH; ++q)
+                        if (k_first + q < K) a.post_soa[(k_first + q) * ld + i] = Ph[q] * inv;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(full + p);
         }
         if (bad_any) atomicOr(a.flags, 1);
-        // cost sums of this producer -> shared scratch after the pipeline drained (below)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             c_pair += __shfl_xor_sync(0xffffffffu, c_pair, o);
@@ -314,25 +310,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
         }
     } else {
         // =============================== CONSUMER ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         const int c = warp;
-        const int tiles = nkt_total * NFT;
-        const int NS = 32 / tiles;
-        const int sub = lane / tiles;
-        const int tl = lane - sub * tiles;
-        const int kt = tl / NFT, ft = tl - kt * NFT;
-        const bool lane_active = sub < NS;
-        double acc[TK][TF];
+        const int g = lane >> 2, t = lane & 3;
+        double acc[NK8][NT][2];
 #pragma unroll
-        for (int i = 0; i < TK; ++i)
+        for (int kt = 0; kt < NK8; ++kt)
 #pragma unroll
-            for (int jj = 0; jj < TF; ++jj) acc[i][jj] = 0.0;
+            for (int ft = 0; ft < NT; ++ft) acc[kt][ft][0] = acc[kt][ft][1] = 0.0;
         constexpr int PPC = kProducers / kConsumers;
         int64_t cnt[PPC];
 #pragma unroll
         for (int q = 0; q < PPC; ++q) {
-            const int64_t g = (int64_t)blockIdx.x * kProducers + (c + q * kConsumers);
-            cnt[q] = n_tiles > g ? (n_tiles - g - 1) / tile_stride_g + 1 : 0;
+            const int64_t gidx = (int64_t)blockIdx.x * kProducers + (c + q * kConsumers);
+            cnt[q] = n_tiles > gidx ? (n_tiles - gidx - 1) / tile_stride_g + 1 : 0;
         }
         for (int64_t j = 0; j < cnt[0]; ++j) {  // cnt[0] >= cnt[q] for every q
 #pragma unroll
@@ -340,30 +331,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
                 if (j < cnt[q]) {
                     const int p = c + q * kConsumers;
                     const double *slot = smem + (size_t)p * slot_doubles;
+                    const double *pa = slot + t * RSP + g;
+                    const double *pb = slot + kTileNodes * RSP + t * RSY + g;
                     mbar_wait(full + p, (uint32_t)(j & 1));
-                    if (lane_active) {
-                        const double *pb = slot + kt * TKs;
-                        const double *yb = slot + kTileNodes * rsp + ft * TFs;
-#pragma unroll 2
-                        for (int nn = sub; nn < kTileNodes; nn += NS) {
-                            double pv[even_up(TK)], yv[even_up(TF)];
 #pragma unroll
-                            for (int cc = 0; cc < even_up(TK); cc += 2) {
-                                const double2 v = *reinterpret_cast<const double2 *>(pb + nn * rsp + cc);
-                                pv[cc] = v.x;
-                                pv[cc + 1] = v.y;
-                            }
+                    for (int ns = 0; ns < kTileNodes / 4; ++ns) {
+                        double av[NK8], bv[NT];
 #pragma unroll
-                            for (int cc = 0; cc < even_up(TF); cc += 2) {
-                                const double2 v = *reinterpret_cast<const double2 *>(yb + nn * RSY + cc);
-                                yv[cc] = v.x;
-                                yv[cc + 1] = v.y;
-                            }
+                        for (int kt = 0; kt < NK8; ++kt) av[kt] = pa[ns * 4 * RSP + 8 * kt];
 #pragma unroll
-                            for (int ii = 0; ii < TK; ++ii)
+                        for (int ft = 0; ft < NT; ++ft) bv[ft] = pb[ns * 4 * RSY + 8 * ft];
 #pragma unroll
-                                for (int jj = 0; jj < TF; ++jj) acc[ii][jj] = fma(pv[ii], yv[jj], acc[ii][jj]);
-                        }
+                        for (int kt = 0; kt < NK8; ++kt)
+#pragma unroll
+                            for (int ft = 0; ft < NT; ++ft) dmma_8x8x4(acc[kt][ft][0], acc[kt][ft][1], av[kt], bv[ft]);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty + p);
@@ -375,19 +356,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
         for (int e0 = threadIdx.x; e0 < KF + 3; e0 += blockDim.x) red[e0] = 0.0;
         __syncthreads();  // (B)
         for (int w = 0; w < kConsumers; ++w) {
-            for (int s = 0; s < NS; ++s) {
-                if (c == w && sub == s && lane_active) {
+            if (c == w) {
 #pragma unroll
-                    for (int ii = 0; ii < TK; ++ii) {
-                        const int k = kt * TK + ii;
+                for (int kt = 0; kt < NK8; ++kt) {
+                    const int k = 8 * kt + g;
 #pragma unroll
-                        for (int jj = 0; jj < TF; ++jj) {
-                            const int f = ft * TF + jj;
-                            if (k < K && f < F) red[k * F + f] += acc[ii][jj];
+                    for (int ft = 0; ft < NT; ++ft)
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const int f = 8 * ft + 2 * t + jj;
+                            if (k < K && f < F) red[k * F + f] += acc[kt][ft][jj];
                         }
-                    }
                 }
-                __syncwarp();
             }
             __syncthreads();
         }
@@ -398,36 +378,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_pipe_kernel(EstepArgs a
     for (int e0 = threadIdx.x; e0 < KF + 3; e0 += blockDim.x) out[e0] = red[e0];
 }
 
-template <int D>
-int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
-    constexpr TileChoice tc = tile_for(D);
-    using C = Cfg<D, tc.tk, tc.tf>;
-    const int nkt_total = (a.K + tc.tk - 1) / tc.tk;
-    if (nkt_total > C::NKT_MAX) return PHMRF_OK;  // needs the multi-pass general kernel
-    const int rsp = pad_row(nkt_total * C::TKs);
-    const size_t slot = (size_t)kTileNodes * (rsp + C::RSY) * sizeof(double);
+template <int D, int NK8>
+int launch_mma(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
+    constexpr int F = n_stat_features(D);
+    constexpr int NT = (F + 7) / 8;
+    if (NK8 * NT * 2 > 64) return PHMRF_OK;  // accumulator tiles would not fit the consumer's registers
+    constexpr int RSP = 8 * NK8 + 4, RSY = 8 * NT + 4;
+    const size_t slot = (size_t)kTileNodes * (RSP + RSY) * sizeof(double);
     size_t smem = kProducers * slot + 2 * kProducers * sizeof(uint64_t);
-    const size_t red_bytes = ((size_t)a.K * C::F + 3) * sizeof(double);
+    const size_t red_bytes = ((size_t)a.K * F + 3) * sizeof(double);
     if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return PHMRF_OK;
     const int64_t n_tiles = (a.n + kTileNodes - 1) / kTileNodes;
     int64_t want = (n_tiles + kProducers - 1) / kProducers;
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
-    const int kth = (nkt_total + 1) / 2;
-    void (*kern)(EstepArgs, int, int) = nullptr;
-    switch (kth) {
-        case 1: kern = estep_pipe_kernel<D, tc.tk, tc.tf, 1>; break;
-        case 2: kern = estep_pipe_kernel<D, tc.tk, tc.tf, 2>; break;
-        case 3: kern = estep_pipe_kernel<D, tc.tk, tc.tf, 3>; break;
-        case 4: kern = estep_pipe_kernel<D, tc.tk, tc.tf, 4>; break;
-        default: return PHMRF_OK;  // more than 8 k tiles: general kernel
-    }
+    auto kern = estep_mma_kernel<D, NK8>;
     PHMRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kPipeThreads, smem, s>>>(a, nkt_total, rsp);
+    kern<<<grid, kPipeThreads, smem, s>>>(a);
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     *handled = true;
     return launch_estep_finalize(a.partials, grid, a.K, D, a.stats_out, s);
+}
+
+template <int D>
+int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
+    switch ((a.K + 7) / 8) {
+        case 1: return launch_mma<D, 1>(a, sm_count, s, handled);
+        case 2: return launch_mma<D, 2>(a, sm_count, s, handled);
+        case 3: return launch_mma<D, 3>(a, sm_count, s, handled);
+        case 4: return launch_mma<D, 4>(a, sm_count, s, handled);
+        case 5: return launch_mma<D, 5>(a, sm_count, s, handled);
+        default: return PHMRF_OK;  // K > 40: general kernel
+    }
 }
 
 }  // namespace
