@@ -11,10 +11,9 @@
 //               shared-memory wavefronts than the DFMA formulation it replaced (ncu: LSU
 //               wavefronts were at 72 % of peak and the sub-partition issue port was the
 //               limiter, see profiles/r1_history.md).
-//   warps 4-15  PRODUCERS: the latency-bound per-node work -- neighbour gather, soft-max
-//               terms, cost scalars, feature row -- for tiles of 16 nodes, two lanes per node
-//               (each lane takes half the states).
-// A producer owns one shared-memory slot (16 P rows + 16 Y rows); producer p feeds consumer
+//   warps 4-11  PRODUCERS: the latency-bound per-node work -- neighbour gather, soft-max
+//               terms, cost scalars, feature row -- for tiles of 32 nodes, one lane per node.
+// A producer owns one shared-memory slot (32 P rows + 32 Y rows); producer p feeds consumer
 // p % 4 through a full/empty mbarrier pair.
 // Same arithmetic as kernels_b.cu (reference: phylo_hmrf.py:311-314, 334-468).
 #include "estep_common.cuh"
@@ -26,9 +25,9 @@ using namespace estep;
 namespace {
 
 constexpr int kConsumers = 4;
-constexpr int kProducers = 12;
+constexpr int kProducers = 8;
 constexpr int kPipeThreads = 32 * (kConsumers + kProducers);
-constexpr int kTileNodes = 16;
+constexpr int kTileNodes = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -91,15 +90,14 @@ __device__ __forceinline__ void write_yd_chunks(double *Yrow, const double (&x)[
      ...);
 }
 
-// NK8 = number of 8-state tiles (K <= 8*NK8); each producer half-lane owns KH = 4*NK8 states.
+// NK8 = number of 8-state tiles (K <= 8*NK8).
 template <int D, int NK8>
 __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a) {
     constexpr int F = n_stat_features(D);
     constexpr int NT = (F + 7) / 8;        // 8-feature tiles
     constexpr int KP = 8 * NK8, FP = 8 * NT;
     constexpr int RSP = KP + 4, RSY = FP + 4;  // == 4 (mod 8): the DMMA operand loads are conflict free
-    constexpr int KH = KP / 2;
-    constexpr int EB = 4;                   // exponentials evaluated in lock step
+    constexpr int EB = 8;                   // exponentials evaluated in lock step
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int slot_doubles = kTileNodes * (RSP + RSY);
@@ -122,31 +120,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
 
     if (warp >= kConsumers) {
         // =============================== PRODUCER ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
         const int p = warp - kConsumers;
         double *slot = smem + (size_t)p * slot_doubles;
-        const int nd = lane & 15, hs = lane >> 4;
-        double *Prow = slot + nd * RSP;
-        double *Yrow = slot + kTileNodes * RSP + nd * RSY;
+        double *Prow = slot + lane * RSP;
+        double *Yrow = slot + kTileNodes * RSP + lane * RSY;
         const bool weighted = a.estimate_type == 3;
         const double beta = a.beta;
-        const int k_first = hs * KH;
         double c_pair = 0.0, c_pwn = 0.0, c_un = 0.0;
         int bad_any = 0;
         int64_t j = 0;
         for (int64_t T = (int64_t)blockIdx.x * kProducers + p; T < n_tiles; T += tile_stride_g, ++j) {
-            const int64_t i_raw = T * kTileNodes + nd;
+            const int64_t i_raw = T * kTileNodes + lane;
             const bool valid = i_raw < n;
             const int64_t i = valid ? i_raw : n - 1;
-            {   // pull this producer's next tile towards L2 (one 128-byte line per row and tile)
+            {   // pull this producer's next tile towards L2 (two 128-byte lines per row and tile)
                 const int64_t T2 = T + tile_stride_g;
                 if (T2 < n_tiles) {
                     const int64_t i2 = T2 * kTileNodes;
-                    const double *row = a.logp + lane * ld + i2;
-                    if (lane < K) prefetch_l2(row);
-                    if (lane + 32 < K) prefetch_l2(row + 32 * ld);
-                    if (lane < D) prefetch_l2(a.X_soa + lane * ld + i2);
-                    if (lane < W) prefetch_l2(a.nbr_w + lane * ld + i2);
+                    for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (q >> 1) * ld + i2 + (q & 1) * 16);
+                    if (lane < 2 * D) prefetch_l2(a.X_soa + (lane >> 1) * ld + i2 + (lane & 1) * 16);
+                    if (lane < 2 * W) prefetch_l2(a.nbr_w + (lane >> 1) * ld + i2 + (lane & 1) * 16);
                     if (lane < W) prefetch_l2(a.nbr_id + lane * ld + i2);
                 }
             }
@@ -174,14 +168,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
                 for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1;
                 lp_li = a.logp[li * ld + i];
             }
-            // this lane's share of the log-likelihood row (registers; issued before the
-            // neighbour arithmetic so that its latency overlaps)
-            double e[KH];
+            // the node's log-likelihood row (registers; issued before the neighbour arithmetic so
+            // that its latency overlaps)
+            double e[KP];
             {
-                const double *pk = a.logp + (int64_t)k_first * ld + i;
+                const double *pk = a.logp + i;
 #pragma unroll
-                for (int q = 0; q < KH; ++q) {
-                    e[q] = (k_first + q) < K ? *pk : -1.0e6;
+                for (int q = 0; q < KP; ++q) {
+                    e[q] = q < K ? *pk : -1.0e6;
                     pk += ld;
                 }
             }
@@ -206,15 +200,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             // high words (3 integer instructions per value instead of an FP64 compare/select).
             int kmax = (int)0x80000000;
 #pragma unroll
-            for (int q = 0; q < KH; ++q) {
+            for (int q = 0; q < KP; ++q) {
                 const int h = __double2hiint(e[q]);
                 kmax = max(kmax, h ^ ((h >> 31) & 0x7fffffff));
             }
-            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, 16));
             const double lpmax = __hiloint2double(kmax ^ ((kmax >> 31) & 0x7fffffff), 0);
             const double shift = fmax(lp_li, lpmax - 598.0);
 #pragma unroll
-            for (int q0 = 0; q0 < KH; q0 += EB) {
+            for (int q0 = 0; q0 < KP; q0 += EB) {
                 double tb[EB];
 #pragma unroll
                 for (int u = 0; u < EB; ++u) tb[u] = e[q0 + u] - shift;
@@ -226,32 +219,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             // ---- slot: wait until the consumer released it.  The P row first holds
             // G_k = exp(S_k), S_k = sum of beta*w over the neighbours labelled k, built by
             // multiplying g_s into G[label_s] slot by slot (no duplicate-label bookkeeping:
-            // exp(a)exp(b) = exp(a+b)); each half-lane owns the states of its own half.
+            // exp(a)exp(b) = exp(a+b)).
             if (j > 0) mbar_wait_relaxed(empty + p, (uint32_t)((j - 1) & 1));
-            double *Ph = Prow + k_first;
 #pragma unroll
-            for (int c = 0; c < KH; c += 2) *reinterpret_cast<double2 *>(Ph + c) = make_double2(1.0, 1.0);
+            for (int c = 0; c < KP; c += 2) *reinterpret_cast<double2 *>(Prow + c) = make_double2(1.0, 1.0);
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                if (lab[s] >= 0 && (lab[s] >= KH) == (hs != 0)) Prow[lab[s]] *= sw[s];
+                if (lab[s] >= 0) Prow[lab[s]] *= sw[s];
             }
+            const double g_li = Prow[li];
             // e_k = exp(logp_k - shift) * G_k, written over G; Q = sum_k G_k on the way
-            double esum = 0.0, qsum = 0.0, g_li = 0.0;
+            double esum = 0.0, qsum = 0.0;
 #pragma unroll
-            for (int c = 0; c < KH; c += 2) {
-                double2 v = *reinterpret_cast<const double2 *>(Ph + c);
-                if (k_first + c < K) qsum += v.x;
-                if (k_first + c + 1 < K) qsum += v.y;
-                g_li = (k_first + c) == li ? v.x : g_li;
-                g_li = (k_first + c + 1) == li ? v.y : g_li;
+            for (int c = 0; c < KP; c += 2) {
+                double2 v = *reinterpret_cast<const double2 *>(Prow + c);
+                if (c < K) qsum += v.x;
+                if (c + 1 < K) qsum += v.y;
                 v.x *= e[c];
                 v.y *= e[c + 1];
                 esum += v.x + v.y;
-                *reinterpret_cast<double2 *>(Ph + c) = v;
+                *reinterpret_cast<double2 *>(Prow + c) = v;
             }
-            esum += __shfl_xor_sync(0xffffffffu, esum, 16);
-            qsum += __shfl_xor_sync(0xffffffffu, qsum, 16);
-            g_li += __shfl_xor_sync(0xffffffffu, g_li, 16);
             // soft-max of -pp at the node's own label: exp(S_li) / sum_k exp(S_k)
             const double pwn_log = log(g_li / qsum + 1e-16);
             const bool bad = !(esum <= DBL_MAX) || !(qsum <= DBL_MAX) || !(esum > 0.0);
@@ -267,13 +255,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
                 }
 #pragma unroll
                 for (int jx = 0; jx < D; ++jx) xs[jx] = x[jx] * inv;
-                constexpr int NCH = FP / 2, H0 = NCH / 2;
-                if (hs == 0)
-                    write_yd_chunks<D, 0>(Yrow, x, xs, inv, std::make_integer_sequence<int, H0>{});
-                else
-                    write_yd_chunks<D, H0>(Yrow, x, xs, inv, std::make_integer_sequence<int, NCH - H0>{});
+                write_yd_chunks<D, 0>(Yrow, x, xs, inv, std::make_integer_sequence<int, FP / 2>{});
             }
-            if (valid && hs == 0) {
+            if (valid) {
                 c_pair += all_neg < 0 ? 0.0 : pc;
                 c_un += lp_li;
                 c_pwn += pwn_log;
@@ -281,8 +265,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             if (a.post_soa != nullptr) {
                 if (valid) {
 #pragma unroll
-                    for (int q = 0; q < KH; ++q)
-                        if (k_first + q < K) a.post_soa[(k_first + q) * ld + i] = Ph[q] * inv;
+                    for (int q = 0; q < KP; ++q)
+                        if (q < K) a.post_soa[q * ld + i] = Prow[q] * inv;
                 }
             }
             __syncwarp();

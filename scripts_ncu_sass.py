@@ -9,7 +9,11 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
 hdr = rows[hi]
-body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+body = []
+for r in rows[hi + 1:]:
+    if len(r) != len(hdr) or r == hdr:
+        break
+    body.append(r)
 si, src = hdr.index("# Samples"), hdr.index("Source")
 stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[si] or 0) for r in body)
