@@ -80,18 +80,22 @@ int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t 
 // node-state and NPT*d(d+3)/2 DFMA per (PS+1)/2 shared loads.  (A first version indexed
 // the constant bank with the state id: ncu showed the ADU pipe at 81 % and the FP64 pipe
 // at 20 % -- indexed LDC is the wrong tool for per-state tables.)
+// The FP64 pipe then saturates at ~75 %: a DFMA with three distinct vector-register
+// operands is register-file limited to 27.4 TFLOP/s on B200 (csrc/probe.cu, probe 6), which
+// is what this kernel reaches.  Passing the factors as kernel parameters (constant-bank /
+// uniform-register multiplier, two vector operands) was tried and measured slower: 204
+// registers -> 8 warps/SM, LDCU traffic on the ADU pipe, 63 % FP64 (profiles/r1_history.md).
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long abs_bits(double v) {
     return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
 }
 
-template <int D, bool SMEM_MODEL>
-__global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs, int64_t n, int64_t ld, int K,
+template <int D, bool SMEM_MODEL, int NPT>
+__global__ void __launch_bounds__(NPT == 8 ? 128 : 256) emit_kernel(const double *__restrict__ Xs, int64_t n, int64_t ld, int K,
                                                     const double *__restrict__ model, double *__restrict__ logp,
                                                     unsigned long long *absmax_bits) {
     constexpr int PS = model_stride(D);
     constexpr int PSs = (PS + 1) & ~1;  // even stride: every state starts 16-byte aligned
-    constexpr int NPT = 4;
     extern __shared__ __align__(16) double smodel[];
     if (SMEM_MODEL) {
         for (int e = threadIdx.x; e < K * PSs; e += blockDim.x) {
@@ -109,12 +113,12 @@ __global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs
         double x[NPT][D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            const double2 v0 = *reinterpret_cast<const double2 *>(Xs + j * ld + i0);
-            const double2 v1 = *reinterpret_cast<const double2 *>(Xs + j * ld + i0 + 2);
-            x[0][j] = v0.x;
-            x[1][j] = v0.y;
-            x[2][j] = v1.x;
-            x[3][j] = v1.y;
+#pragma unroll
+            for (int u = 0; u < NPT; u += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(Xs + j * ld + i0 + u);
+                x[u][j] = v.x;
+                x[u + 1][j] = v.y;
+            }
         }
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
@@ -153,8 +157,9 @@ __global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs
             double l[NPT];
 #pragma unroll
             for (int u = 0; u < NPT; ++u) l[u] = -acc[u];
-            *reinterpret_cast<double2 *>(logp + k * ld + i0) = make_double2(l[0], l[1]);
-            *reinterpret_cast<double2 *>(logp + k * ld + i0 + 2) = make_double2(l[2], l[3]);
+#pragma unroll
+            for (int u = 0; u < NPT; u += 2)
+                *reinterpret_cast<double2 *>(logp + k * ld + i0 + u) = make_double2(l[u], l[u + 1]);
 #pragma unroll
             for (int u = 0; u < NPT; ++u) {
                 const unsigned long long b = (i0 + u < n) ? abs_bits(l[u]) : 0ull;
@@ -183,18 +188,19 @@ template <int D>
 static int launch_emit_d(const double *Xs, int64_t n, int64_t ld, int K, const double *model, double *logp,
                          unsigned long long *absmax_bits, int sm_count, cudaStream_t s) {
     constexpr int PSs = (model_stride(D) + 1) & ~1;
-    const int64_t n_groups = (n + 3) / 4;
-    const int64_t blocks = (n_groups + 255) / 256;
+    constexpr int NPT = 4, TPB = 256;  // 8 nodes/thread measured identical (register-file bound either way)
+    const int64_t n_groups = (n + NPT - 1) / NPT;
+    const int64_t blocks = (n_groups + TPB - 1) / TPB;
     const int64_t cap = (int64_t)sm_count * 4;
     int grid = (int)(blocks < cap ? blocks : cap);
     if (grid < 1) grid = 1;
     const size_t smem = (size_t)K * PSs * sizeof(double);
-    if (smem <= 160 * 1024) {
+    if (smem <= 100 * 1024) {
         if (smem > 48 * 1024)
-            PHMRF_CUDA(cudaFuncSetAttribute(emit_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        emit_kernel<D, true><<<grid, 256, smem, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
+            PHMRF_CUDA(cudaFuncSetAttribute(emit_kernel<D, true, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_kernel<D, true, NPT><<<grid, TPB, smem, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
     } else {
-        emit_kernel<D, false><<<grid, 256, 0, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
+        emit_kernel<D, false, NPT><<<grid, TPB, 0, s>>>(Xs, n, ld, K, model, logp, absmax_bits);
     }
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
