@@ -57,6 +57,17 @@ def emit_flops_per_node_state(d):
     return d * d + 3 * d + 2
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture of this workload (profiles/r1_traffic.json); None if the
+    workload was not captured."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return table[workload][kernel]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
 
@@ -304,9 +315,9 @@ def run_ours(args):
     b_s = phase_ms[2] * 1e-3
     b_tflops = n * K * estep_flops_per_node_state(d) / b_s / 1e12
     roofline = {
-        "kernel": "estep_kernel (phase B: posteriors+costs+statistics)",
+        "kernel": "estep_mma_kernel (phase B: posteriors+costs+statistics, csrc/kernels_b2.cu)",
         "bound": bound, "achieved": b_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": b_tflops / fp64_peak,
-        "traffic": None,
+        "traffic": ncu_traffic(args.workload, "estep"),
         "peak_source": "DFMA-chain probe in this run (csrc/probe.cu); HBM %s" % hbm_src,
         "kernel_share_of_step": phase_ms[2] / phase_ms.sum(),
         "phase_ms": {"A1_emit": phase_ms[0], "A2_quantise": phase_ms[1], "B_estep": phase_ms[2]},
