@@ -154,6 +154,19 @@ int phmrf_estep_stats_async(phmrf_region *r, int estimate_type);
 /* Number of kernel launches this library has enqueued so far (bench "gpu_launches"). */
 int64_t phmrf_launch_count(void);
 
+/* ------------------------------------------------------------------ next row (f-1) ---- */
+
+/* utility.py:1871-1973 (edge_weightlist_grid3_undirected_unsym, kind=1: diagonal region of
+ * n2 bins, row-major upper triangle incl. the diagonal) and utility.py:1975-2053
+ * (edge_weightlist_grid3_undirected, kind=0: n1 x n2 rectangle): the undirected 8- or
+ * 4-neighbourhood edge list of a DENSE region with d_ij = |xi-xj|^2/(|xi||xj|+1e-16) (halved
+ * between two diagonal nodes), sorted by (id1,id2), in the reference's [E,3] float64 format
+ * (id1, id2, d_ij).  X is the host [n,d] feature matrix in the region's node order.
+ * phmrf_grid_edge_count gives E (closed form) so the caller can size edge_list_out. */
+int64_t phmrf_grid_edge_count(int kind, int64_t n1, int64_t n2, int num_neighbor);
+int phmrf_grid_edges(int device, const double *X, int n_features, int kind, int64_t n1, int64_t n2, int num_neighbor,
+                     double *edge_list_out, int64_t n_edges);
+
 /* ------------------------------------------------------------------ probes ------------ */
 
 /* FP64 FMA-pipe peak of the current device, measured with a dependent-chain DFMA

@@ -60,6 +60,9 @@ SIGNATURES = {
     "phmrf_quantise_async": (C.c_int, [_vp, C.c_double, C.c_double]),
     "phmrf_estep_stats_async": (C.c_int, [_vp, C.c_int]),
     "phmrf_launch_count": (C.c_int64, []),
+    "phmrf_grid_edge_count": (C.c_int64, [C.c_int, C.c_int64, C.c_int64, C.c_int]),
+    "phmrf_grid_edges": (C.c_int, [C.c_int, _c_double_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _c_double_p,
+                                   C.c_int64]),
     "phmrf_probe_fp64_tflops": (C.c_int, [C.c_int, _c_double_p]),
     "phmrf_probe": (C.c_int, [C.c_int, C.c_int, _c_double_p]),
 }

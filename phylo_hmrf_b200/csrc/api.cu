@@ -654,6 +654,47 @@ int phmrf_set_logprob(phmrf_region *r, const double *logprob) {
     return PHMRF_OK;
 }
 
+// ---------------------------------------------------------------- next row (f-1)
+int64_t phmrf_grid_edge_count(int kind, int64_t n1, int64_t n2, int num_neighbor) {
+    if ((kind != 0 && kind != 1) || n1 < 1 || n2 < 1 || (num_neighbor != 8 && num_neighbor != 4)) return -1;
+    if (kind == 1 && n1 != n2) return -1;
+    return grid_edge_count(kind, n1, n2, num_neighbor);
+}
+
+int phmrf_grid_edges(int device, const double *X, int n_features, int kind, int64_t n1, int64_t n2, int num_neighbor,
+                     double *edge_list_out, int64_t n_edges) {
+    const int64_t expect = phmrf_grid_edge_count(kind, n1, n2, num_neighbor);
+    if (!X || n_features < 1 || expect < 0 || n_edges != expect || (n_edges > 0 && !edge_list_out)) {
+        set_error("phmrf_grid_edges: invalid arguments (kind 0/1, num_neighbor 8/4, n_edges from phmrf_grid_edge_count)");
+        return PHMRF_E_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        set_error("phmrf_grid_edges: no such CUDA device (this library has no CPU fallback)");
+        return PHMRF_E_CUDA;
+    }
+    PHMRF_CUDA(cudaSetDevice(device));
+    const int64_t n = kind == 1 ? n2 * (n2 + 1) / 2 : n1 * n2;
+    double *dX = nullptr, *dE = nullptr;
+    PHMRF_CUDA(cudaMalloc((void **)&dX, sizeof(double) * n * n_features));
+    if (cudaMalloc((void **)&dE, sizeof(double) * 3 * (n_edges > 0 ? n_edges : 1)) != cudaSuccess) {
+        cudaFree(dX);
+        return cuda_fail(cudaGetLastError(), "cudaMalloc(edge list)", __FILE__, __LINE__);
+    }
+    int rc = PHMRF_OK;
+    if (cudaMemcpy(dX, X, sizeof(double) * n * n_features, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "upload X", __FILE__, __LINE__);
+    if (rc == PHMRF_OK && n_edges > 0)
+        rc = launch_grid_edges(dX, kind, n1, n2, num_neighbor, n_features, n, n_edges, dE, nullptr);
+    if (rc == PHMRF_OK && n_edges > 0 &&
+        cudaMemcpy(edge_list_out, dE, sizeof(double) * 3 * n_edges, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "download edge list", __FILE__, __LINE__);
+    cudaFree(dX);
+    cudaFree(dE);
+    return rc;
+}
+
 // ---------------------------------------------------------------- probes
 int phmrf_probe(int device, int which, double *out) {
     if (!out) return PHMRF_E_INVALID;

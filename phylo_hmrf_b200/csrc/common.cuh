@@ -80,6 +80,11 @@ int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *ha
 // Fold per-block partials into stats_out (defined in kernels_b.cu).
 int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, double *stats_out, cudaStream_t s);
 
+// ---- region edge lists on the GPU (kernels_grid.cu) ----------------------
+long long grid_edge_count(int kind, long long n1, long long n2, int nn);
+int launch_grid_edges(const double *X_dev, int kind, long long n1, long long n2, int nn, int D, long long n,
+                      long long n_edges, double *edge_list_dev, cudaStream_t s);
+
 // ---- probes (probe.cu) ----------------------------------------------------------------
 int run_probe(int which, double *out);
 

@@ -183,6 +183,34 @@ def make_case(name, seed, regions, d, K, beta, beta1, estimate_type, isolate=())
     print("wrote", name, "N =", len(X_all), "E =", [len(e) for e in els])
 
 
+def make_edge_cases():
+    """Pure geometry fixtures: the reference's two edge-list builders on dense regions."""
+    util = ref_loader.load_utility(["mapping_Idx", "_sort_array", "edge_weightlist_grid3_undirected_unsym",
+                                    "edge_weightlist_grid3_undirected"])
+    rng = np.random.default_rng(77)
+    out = {}
+    # (the reference crashes when a direction has no candidate at all, e.g. a 2-bin triangle:
+    # mapping_Idx indexes an empty array, utility.py:846 -- so the smallest shapes here are 3 / 2x3)
+    cases = [("tri", 13, 13, 8, 4), ("tri", 9, 9, 4, 3), ("tri", 3, 3, 8, 2), ("rect", 6, 8, 8, 5),
+             ("rect", 5, 7, 4, 2), ("rect", 2, 3, 8, 3)]
+    for c, (kind, n1, n2, nn, d) in enumerate(cases):
+        if kind == "tri":
+            serial = np.asarray([i * n2 + j for i in range(n1) for j in range(i, n2)])
+            X = synth_features(rng, len(serial), d)
+            el = util["edge_weightlist_grid3_undirected_unsym"](X, serial, n2, '', nn)
+        else:
+            serial = np.asarray([i * n2 + j for i in range(n1) for j in range(n2)])
+            X = synth_features(rng, len(serial), d)
+            el = util["edge_weightlist_grid3_undirected"](X, serial, (n1, n2), '', nn)
+        out["c%d_meta" % c] = np.asarray([1 if kind == "tri" else 0, n1, n2, nn, d])
+        out["c%d_X" % c] = X
+        out["c%d_serial" % c] = serial
+        out["c%d_edge_list" % c] = np.asarray(el, dtype=np.float64).reshape(-1, 3)
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "edges_cases.npz"), **out)
+    print("wrote edges_cases", [len(out["c%d_edge_list" % c]) for c in range(len(cases))])
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present; fixtures can only be regenerated in the build container")
@@ -192,6 +220,7 @@ def main():
     make_case("case_unweighted_iso", 303, [("diag", 10, 10)], d=3, K=4, beta=2.0, beta1=0.1, estimate_type=0,
               isolate=((0, 23),))
     make_case("case_d9_k30", 404, [("diag", 16, 16)], d=9, K=30, beta=1.0, beta1=0.1, estimate_type=3)
+    make_edge_cases()
 
 
 if __name__ == "__main__":
