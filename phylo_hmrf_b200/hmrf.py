@@ -261,6 +261,129 @@ class phyloHMRF(object):
         stats['obs*obs.T'] += stats1['obs*obs.T']
         return stats
 
+    # ------------------------------------------------------------------ EM driver
+    def _init(self, X, lengths=None):
+        """phylo_hmrf.py:205-264 (MiniBatchKMeans labels, per-cluster OU fit).  Out of the
+        hot-path scope: supply `init_fn(model, X)` (it must set means_, _covars_, params_vec1,
+        labels, labels_local) or subclass."""
+        if getattr(self, "init_fn", None) is None:
+            raise NotImplementedError("initialisation is outside the re-hosted hot path: set model.init_fn")
+        self.init_fn(self, X)
+
+    def _check(self):
+        """base.py:515-538 / phylo_hmrf.py:152-182: parameter validation before fitting."""
+        K, d = self.n_components, self.n_features
+        self.means_ = np.asarray(self.means_)
+        if self.means_.shape != (K, d):
+            raise ValueError("means_ must have shape (n_components, n_features)")
+        if np.asarray(self._covars_).shape != (K, d, d):
+            raise ValueError("'full' covars must have shape (n_components, n_dim, n_dim)")
+
+    def _do_mstep(self, stats):
+        """phylo_hmrf.py:1500-1528 (K constrained SLSQP fits of the OU tree parameters).  Out of
+        the hot-path scope: supply `mstep_fn(model, stats)` (it must update means_, _covars_
+        and params_vec1) or subclass."""
+        if getattr(self, "mstep_fn", None) is None:
+            raise NotImplementedError("the OU M-step is outside the re-hosted hot path: set model.mstep_fn")
+        self.stats = stats.copy()
+        self.mstep_fn(self, stats)
+
+    def _ou_param_varied_constraint(self, params_vec):
+        """phylo_hmrf.py:985-1036: writes means_/_covars_ for the final parameters; delegated
+        to `finalize_fn(model, params_vec)` when given."""
+        if getattr(self, "finalize_fn", None) is not None:
+            self.finalize_fn(self, params_vec)
+
+    def fit_accumulate_test(self, X, len_vec, threshold, annotation, m_iter, lengths=None, n_threads=None):
+        """base.py:301-455, without fork.  Same iteration, cost aggregation (N_r/N weights,
+        :332-337, :384-396), convergence tests (:402-435) and best-iteration bookkeeping;
+        regions run through `_predict_posteriors` on a thread pool (the GPU kernels and the
+        host graph cut release the GIL), results are gathered from a queue exactly as the
+        parent process does.  Returns (params_vec, params_vec1, params_vecList, iter_id1,
+        iter_id2, cost_vec, t_labels)."""
+        try:
+            import queue as _queue
+        except ImportError:  # py2
+            import Queue as _queue
+        from concurrent.futures import ThreadPoolExecutor
+
+        self._init(X, lengths=lengths)
+        self._check()
+        max_iter = m_iter
+        max_iter1 = 50  # iterations after the previous minimum
+        pairwise_cost_pre, unary_cost_pre, cost1_pre = 0.001, 0.001, 0.001
+        threshold1, threshold2 = threshold, threshold
+        cost_vec = []
+        min_cost = [0, 1000]
+        min_cost1 = [0, 1000]
+        params_vec = self.params_vec1.copy()
+        params_vec1 = self.params_vec1.copy()
+        num_region = len(len_vec)
+        ratio_vec = np.zeros(num_region)
+        for i in range(0, num_region):
+            ratio_vec[i] = len_vec[i][0]
+        n_samples = int(sum(ratio_vec))
+        ratio_vec = ratio_vec * 1.0 / n_samples
+        params_vecList = []
+        t_labels = np.zeros(n_samples)
+        workers = n_threads or min(num_region, 8)
+
+        for iter in range(max_iter):
+            stats = self._initialize_sufficient_statistics()
+            self._sync_model()
+            self.queue = _queue.Queue()
+            if workers > 1 and num_region > 1:
+                with ThreadPoolExecutor(max_workers=workers) as pool:
+                    list(pool.map(lambda r: self._predict_posteriors(X, len_vec, r, self.queue), range(num_region)))
+            else:
+                for region_id in range(0, num_region):
+                    self._predict_posteriors(X, len_vec, region_id, self.queue)
+            results = [self.queue.get() for _ in range(num_region)]
+
+            pairwise_cost1, pairwise_cost, unary_cost, cost1 = 0, 0, 0, 0
+            id1 = 3
+            labels = np.zeros(n_samples)
+            # fixed (region id) order so that the floating-point sums do not depend on thread timing
+            for vec1 in sorted(results, key=lambda v: v[0]):
+                region_id = vec1[0]
+                pairwise_cost1 += vec1[id1] * ratio_vec[region_id]
+                pairwise_cost += vec1[id1 + 1] * ratio_vec[region_id]
+                unary_cost += vec1[id1 + 2] * ratio_vec[region_id]
+                cost1 += vec1[id1 + 3] * ratio_vec[region_id]
+                s1, s2 = len_vec[region_id][1], len_vec[region_id][2]
+                stats = self._accumulate_sufficient_statistics_1(stats, vec1[1])
+                labels[s1:s2] = vec1[2]
+
+            t_difference1 = abs((pairwise_cost - pairwise_cost_pre) * 1.0 / pairwise_cost_pre)
+            t_difference2 = abs((unary_cost - unary_cost_pre) * 1.0 / unary_cost_pre)
+            t_difference3 = abs((cost1 - cost1_pre) * 1.0 / cost1_pre)
+            pairwise_cost_pre, unary_cost_pre, cost1_pre = pairwise_cost, unary_cost, cost1
+            cost_vec.append([iter, pairwise_cost, unary_cost, cost1])
+            params_vecList.append(self.params_vec1.copy())
+            self.labels = labels.copy()
+
+            if cost1 < min_cost[1]:
+                min_cost = [iter, cost1]
+                params_vec = self.params_vec1.copy()
+                self.labels_local = self.labels.copy()  # current local optimal state estimate
+            if cost1 < min_cost1[1] and iter >= 3:
+                min_cost1 = [iter, cost1]
+                params_vec1 = self.params_vec1.copy()
+                t_labels = self.labels.copy()  # keep the estimated labels
+            if ((t_difference1 < threshold1 and t_difference2 < threshold2) or (t_difference3 < threshold1)) and (iter > 5):
+                break
+            if iter > max_iter:
+                break
+            if iter - min_cost1[0] > max_iter1:
+                break
+            self._do_mstep(stats)
+
+        self.params_vec1 = params_vec1.copy()
+        self._ou_param_varied_constraint(params_vec)
+        cost_vec = np.asarray(cost_vec)
+        params_vecList = np.asarray(params_vecList)
+        return params_vec, params_vec1, params_vecList, min_cost[0], min_cost1[0], cost_vec, t_labels
+
     def close(self):
         for reg in self._regions:
             reg.close()

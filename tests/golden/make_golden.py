@@ -211,6 +211,53 @@ def make_edge_cases():
     print("wrote edges_cases", [len(out["c%d_edge_list" % c]) for c in range(len(cases))])
 
 
+def make_fit_driver_cases():
+    """Run the REFERENCE's fit_accumulate_test (base.py:301-455) on scripted stand-ins
+    (fit_script.py); multiprocessing is replaced by an in-line Process/Queue."""
+    import time
+    import fit_script as fs
+
+    class _Q:
+        def __init__(self):
+            self.items = []
+
+        def put(self, x):
+            self.items.append(x)
+
+        def get(self):
+            return self.items.pop(0)
+
+    class _P:
+        def __init__(self, target=None, args=()):
+            self.target, self.args = target, args
+
+        def start(self):
+            self.target(*self.args)
+
+        def join(self):
+            pass
+
+    class _MP:
+        Queue = _Q
+        Process = _P
+
+    g = {"np": np, "time": time, "mp": _MP, "ConvergenceMonitor": lambda *a, **k: None}
+    ref_loader.load_functions("base.py", ["fit_accumulate_test"], 1, g)
+    Ref = type("RefDriver", (fs.ScriptedModel,), {"fit_accumulate_test": g["fit_accumulate_test"]})
+    out = {}
+    for name, (m_iter, thr, _) in fs.SCENARIOS.items():
+        m = Ref()
+        m.script(name)
+        res = m.fit_accumulate_test(np.zeros((fs.N, fs.D)), fs.LEN_VEC, thr, "test", m_iter)
+        params_vec, params_vec1, plist, it1, it2, cost_vec, t_labels = res
+        out.update({name + "_params_vec": params_vec, name + "_params_vec1": params_vec1, name + "_plist": plist,
+                    name + "_it": np.asarray([it1, it2]), name + "_cost_vec": cost_vec, name + "_t_labels": t_labels,
+                    name + "_labels_local": m.labels_local, name + "_final_params_vec1": m.params_vec1,
+                    name + "_finalized_with": m.finalized_with, name + "_n_iter": m.iteration})
+        print("fit driver", name, "iterations", m.iteration, "best", it1, it2)
+    np.savez_compressed(os.path.join(HERE, "fit_driver.npz"), **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present; fixtures can only be regenerated in the build container")
@@ -221,6 +268,7 @@ def main():
               isolate=((0, 23),))
     make_case("case_d9_k30", 404, [("diag", 16, 16)], d=9, K=30, beta=1.0, beta1=0.1, estimate_type=3)
     make_edge_cases()
+    make_fit_driver_cases()
 
 
 if __name__ == "__main__":
