@@ -6,11 +6,12 @@ replaces in the reference (file:line in each docstring), so code written against
 E-step: emission -> integer cost arrays -> graph cut (host GCO) -> posteriors, cost
 scalars and sufficient statistics.
 
-What is *not* here (out of the round-1 scope): the OU tree algebra, the
-K-means/OU initialisation (``_init``) and the SLSQP M-step (``_do_mstep``).  The constructor
-accepts the reference's arguments but only uses those the hot path reads; ``means_`` and
-``_covars_`` are plain attributes the caller (or a later M-step) sets, exactly the two
-arrays ``_do_mstep`` writes back at phylo_hmrf.py:1522-1524.
+The callers either side of the path (SURVEY 8 "next" rows) are re-hosted too: the fork-free EM
+driver ``fit_accumulate_test`` (f-2) and, when the constructor is given the tree
+(``edge_list``), the OU initialisation and SLSQP M-step of ``ou.py`` (f-3), which write
+``means_`` / ``_covars_`` exactly where ``_do_mstep`` does (phylo_hmrf.py:1522-1524).  Without a
+tree, ``means_`` / ``_covars_`` are plain attributes and ``init_fn`` / ``mstep_fn`` hooks can be
+supplied by the caller.
 
 There is no CPU fallback: all arithmetic of the hot path runs in ``libphmrf.so``.
 """
@@ -76,6 +77,14 @@ class phyloHMRF(object):
         self._regions = []
         self._model_key = None
         self._last_logprob = {}
+
+        self.initial_mode, self.initial_w1, self.initial_w1a, self.initial_w2 = (
+            initial_mode, initial_weight, initial_weight1, initial_magnitude)
+        self.init_fn = self.mstep_fn = self.finalize_fn = None
+        if edge_list is not None:
+            # OU tree algebra, initialisation and M-step (host side, phylo_hmrf.py:715-1528)
+            from . import ou
+            ou.attach(self, edge_list, initial_weight, initial_weight1, initial_magnitude, initial_mode, random_state)
 
         self.edge_potential = self._pairwise_potential()
         if observation is not None and len_vec is not None and edge_list_1 is not None:

@@ -258,6 +258,90 @@ def make_fit_driver_cases():
     np.savez_compressed(os.path.join(HERE, "fit_driver.npz"), **out)
 
 
+def make_ou_cases():
+    """Run the REFERENCE's OU tree algebra and M-step objective (phylo_hmrf.py:715-1325) on the
+    shipped example tree and on a 5-leaf caterpillar."""
+    import sys as _sys
+    import tempfile
+    from numpy.linalg import det, inv
+    names = ["_initilize_tree_mtx", "_sub_tree_leaf", "_compute_base_struct", "_compute_covariance_index",
+             "_search_leaf", "_search_ancestor", "_matrix1", "_ou_param_varied_constraint",
+             "_ou_lik_varied_constraint", "_check_params", "_ou_lik_varied_single", "_ou_init_guess"]
+    g = {"np": np, "sys": _sys, "det": det, "inv": inv, "small_eps": 1e-16}
+    ref_loader.load_functions("phylo_hmrf.py", names, 1, g)
+    Ref = type("RefOU", (object,), {n: g[n] for n in names})
+    trees = {"example": np.loadtxt(os.path.join(ref_loader.REF, "example_input", "edge.1.txt"), dtype=int),
+             "caterpillar5": np.asarray([[0, 1], [1, 2], [1, 3], [3, 4], [3, 5], [5, 6], [5, 7], [7, 8], [7, 9]])}
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)  # the reference writes base_mtx_*/ou_A*.txt into the working directory
+        try:
+            for tname, edges in trees.items():
+                rng = np.random.default_rng(len(tname))
+                m = Ref()
+                m.tree_mtx, m.node_num = m._initilize_tree_mtx(edges)
+                m.branch_dim = m.node_num - 1
+                m.n_params = m.node_num + m.branch_dim * 2 + 1
+                m.branch_vec = [None] * m.node_num
+                m.base_struct = [None] * m.node_num
+                m.leaf_list = m._compute_base_struct()
+                m.leaf_vec = m._search_leaf()
+                m.path_vec = m._search_ancestor()
+                m.A1, m.A2, m.pair_list, m.parent_list = m._matrix1()
+                d, K = len(m.leaf_vec), 6
+                m.n_features, m.n_components, m.min_covar = d, K, 1e-3
+                m.n_samples, m.lambda_0 = 5000, 1.0
+                params = rng.random((K, m.n_params))
+                params[1, 1:3] = 1e-9                      # beta below the 1e-7 guard
+                params[2, 1:1 + m.branch_dim] = 50.0       # strong selection: near-diagonal covariance
+                params[3, 1 + m.branch_dim:1 + 2 * m.branch_dim] = 1e-12   # vanishing variance: conditioning ladder
+                params[3, 0] = 1e-13
+                m.means_, m._covars_ = np.zeros((K, d)), np.zeros((K, d, d))
+                m._ou_param_varied_constraint(params)
+                A = rng.random((K, d, d))
+                post = 200 + 800 * rng.random(K)
+                mu_k = rng.random((K, d))
+                m.stats = {'post': post, 'obs': mu_k * post[:, None],
+                           'obs*obs.T': (np.einsum('kij,klj->kil', A, A) + mu_k[:, :, None] * mu_k[:, None, :])
+                           * post[:, None, None]}
+                m.init_ou_params = rng.random((K, m.n_params))
+                liks, vals, cvs = [], [], []
+                for c in range(K):
+                    liks.append(m._ou_lik_varied_constraint(params[c].copy(), c))
+                    vals.append(m.values.copy())
+                    cvs.append(m.cv_mtx.copy())
+                bad = params[0].copy(); bad[2] = 150.0
+                nanp = params[0].copy(); nanp[3] = np.nan; nanp[2] = 150.0
+                lik_nan = m._ou_lik_varied_constraint(nanp.copy(), 0)   # falls back to init_ou_params[0]
+                obs = rng.random((300, d))
+                single = [m._ou_lik_varied_single(params[c].copy(), obs) for c in (0, 2, 4)]
+                single_cv = m.cv_mtx.copy()
+                np.random.seed(11)
+                m.initial_w2 = 0.7
+                guess = m._ou_init_guess(mu_k[0])
+                p = tname + "_"
+                out.update({p + "edges": edges, p + "leaf_vec": m.leaf_vec, p + "A1": m.A1, p + "A2": m.A2,
+                            p + "pair_list": np.asarray(m.pair_list), p + "parent": np.asarray(
+                                [-1 if (isinstance(x, list) and not x) else int(x) for x in m.parent_list]),
+                            p + "path_flat": np.concatenate(m.path_vec), p + "path_len": np.asarray(
+                                [len(x) for x in m.path_vec]),
+                            p + "leaf_rank": np.asarray([m.leaf_list[int(l)] for l in m.leaf_vec]),
+                            p + "params": params, p + "means": m.means_.copy(), p + "covars": m._covars_.copy(),
+                            p + "post": post, p + "obs": m.stats['obs'], p + "obsobsT": m.stats['obs*obs.T'],
+                            p + "init_ou_params": m.init_ou_params, p + "liks": np.asarray(liks),
+                            p + "values": np.asarray(vals), p + "cv_mtx": np.asarray(cvs),
+                            p + "check": np.asarray([m._check_params(params[0]), m._check_params(bad),
+                                                     m._check_params(nanp)]),
+                            p + "bad": bad, p + "nanp": nanp, p + "lik_nan": lik_nan, p + "single_obs": obs,
+                            p + "single": np.asarray(single), p + "single_cv": single_cv, p + "guess": guess,
+                            p + "guess_mean": mu_k[0]})
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "ou_cases.npz"), **out)
+    print("wrote ou_cases")
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present; fixtures can only be regenerated in the build container")
@@ -269,6 +353,7 @@ def main():
     make_case("case_d9_k30", 404, [("diag", 16, 16)], d=9, K=30, beta=1.0, beta1=0.1, estimate_type=3)
     make_edge_cases()
     make_fit_driver_cases()
+    make_ou_cases()
 
 
 if __name__ == "__main__":

@@ -59,3 +59,32 @@ def test_em_driver_end_to_end_two_regions():
     # labels_local is the labelling of the best iteration and feeds the next graph cut (quirk 9)
     assert model.labels_local.shape == (len(X),)
     model.close()
+
+
+def test_em_with_ou_mstep_on_example_tree():
+    """The whole per-iteration chain of the reference on the shipped example tree (4 leaves):
+    K-means + OU initial fits, GPU E-step, host GCO swap, OU/SLSQP M-step (ou.py)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import phylo_hmrf_b200 as ph
+    from phylo_hmrf_b200 import synth, utility
+    tree_edges = np.array([[0, 1], [1, 2], [1, 3], [3, 4], [4, 5], [4, 6], [3, 7]])  # example_input/edge.1.txt
+    d, K = 4, 3
+    g = synth.make_band(5, 36, d)
+    X = g["X_own"]
+    len_vec = [[len(X), 0, len(X), 36, 36, 0, 0, 0, 1, 21]]
+    els = [utility.edge_weightlist_grid3_undirected_unsym(X, g["x"] * 36 + g["y"], 36, '', 8)]
+    model = ph.phyloHMRF(len(X), d, edge_list=tree_edges, branch_list=np.ones(7), cons_param=1, beta=1.0, beta1=0.1,
+                         observation=X, edge_list_1=els, len_vec=len_vec, n_components=K, estimate_type=3,
+                         random_state=3)
+    assert model.n_params == 23
+    res = model.fit_accumulate_test(X, len_vec, 1e-3, "test", 8)
+    params_vec, params_vec1, plist, it1, it2, cost_vec, t_labels = res
+    assert params_vec.shape == (K, 23) and np.isfinite(cost_vec).all() and len(cost_vec) >= 7
+    assert model.tree.check_params(params_vec[0]) == 1
+    assert model.means_.shape == (K, d) and model._covars_.shape == (K, d, d)
+    for c in range(K):
+        assert np.linalg.eigvalsh(model._covars_[c]).min() > 0
+    assert t_labels.shape == (len(X),)
+    model.close()
