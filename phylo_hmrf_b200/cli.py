@@ -1,0 +1,80 @@
+"""Command line of the reference (`python phylo_hmrf.py ...`, phylo_hmrf.py:1531-1760) over the
+re-hosted model: same option names and code defaults, same cache files, same
+`.mat` result.  Raw Hi-C loading / image filtering (utility.py) is not re-hosted:
+run with `--reload 1` on the `data.*.npy` / `edgelist.*.npy` / `lenvec.*.txt` caches the
+reference writes (phylo_hmrf.py:1697-1704)."""
+from __future__ import annotations
+
+import os
+from optparse import OptionParser
+
+import numpy as np
+
+
+def parse_args(argv=None):
+    """phylo_hmrf.py:1531-1568 (33 options; the code defaults, not the README's)."""
+    parser = OptionParser(usage="Phylo-HMRF state estimation", add_help_option=False)
+    for flags, default in [
+        (("-n", "--num_states"), "10"), (("-f", "--chromosome"), "1"), (("-l", "--length"), "one"),
+        (("-p", "--root_path"), "."), (("-m", "--multiple"), "true"), (("-a", "--species_name"), "human"),
+        (("-o", "--sort_states"), "false"), (("-r", "--run_id"), "0"), (("-c", "--cons_param"), "1"),
+        (("-t", "--method_mode"), "1"), (("-d", "--initial_mode"), "0"), (("-i", "--initial_weight"), "0.3"),
+        (("-k", "--initial_weight1"), "0.1"), (("-j", "--initial_magnitude"), "1"), (("-s", "--simu_version"), "1"),
+        (("-u", "--position1"), "0"), (("-v", "--position2"), "50000"), (("-w", "--filter_sigma"), "0.25"),
+        (("-b", "--beta"), "1"), (("--beta1",), "0.5"), (("--num_neighbor",), "8"), (("--filter_mode",), "0"),
+        (("-e", "--threshold"), "0.001"), (("-g", "--estimate_type"), "0"), (("-q", "--annotation"), "test"),
+        (("--dtype",), "0"), (("--reload",), "0"), (("--quantile",), "1"), (("--miter",), "60"),
+        (("--resolution",), "50000"), (("--ref_species",), "hg38"), (("--chromvec",), "1"), (("--output",), "."),
+    ]:
+        parser.add_option(*flags, default=default)
+    opts, _ = parser.parse_args(argv)
+    return opts
+
+
+def _read_table(path, cast):
+    with open(path) as f:
+        return [[cast(v) for v in line.split('\t')] for line in f if line.strip()]
+
+
+def run(opts, device=0):
+    """phylo_hmrf.py:1570-1749 for `--reload 1`.  Returns the dict written to the `.mat` file."""
+    import scipy.io
+    from .hmrf import phyloHMRF
+    run_id, K = int(opts.run_id), int(opts.num_states)
+    cons_param = float(opts.cons_param)
+    resolution = int(opts.resolution)
+    data_path, output_path = str(opts.root_path), str(opts.output)
+    edge_list = _read_table("%s/edge.1.txt" % data_path, int)
+    bl = "%s/branch_length.1.txt" % data_path
+    branch_list = _read_table(bl, float)[0] if os.path.exists(bl) else None
+    stem = "%dKb.observed.%d" % (resolution // 1000, run_id)
+    f1, f2, f3 = ("%s/data.%s.npy" % (output_path, stem), "%s/edgelist.%s.npy" % (output_path, stem),
+                  "%s/lenvec.%s.txt" % (output_path, stem))
+    if int(opts.reload) != 1 or not all(os.path.exists(f) for f in (f1, f2, f3)):
+        raise SystemExit("raw Hi-C loading is not re-hosted (SURVEY 8 f-4): run with --reload 1 and the cache files "
+                         "%s, %s, %s in --output" % (f1, f2, f3))
+    samples = np.load(f1)
+    edge_list_vec = list(np.load(f2, allow_pickle=True))
+    len_vec = np.atleast_2d(np.loadtxt(f3, dtype='int32', delimiter='\t')).tolist()
+    if int(opts.method_mode) != 1:
+        raise SystemExit("method_mode 1 (Phylo-HMRF) is the only mode of the reference's run()")
+    model = phyloHMRF(n_components=K, run_id=run_id, n_samples=samples.shape[0], n_features=samples.shape[-1],
+                      observation=samples, edge_list=edge_list, len_vec=len_vec, type_id=int(opts.simu_version),
+                      branch_list=branch_list, edge_list_1=edge_list_vec, cons_param=cons_param, beta=float(opts.beta),
+                      beta1=float(opts.beta1), initial_mode=int(opts.initial_mode),
+                      initial_weight=float(opts.initial_weight), initial_weight1=float(opts.initial_weight1),
+                      initial_magnitude=float(opts.initial_magnitude), learning_rate=0.001,
+                      estimate_type=int(opts.estimate_type), max_iter=100, n_iter=5000, tol=1e-7, device=device)
+    filename = "%s/estimate_ou_%d_%.2f_%d_%s" % (output_path, run_id, cons_param, K, str(opts.annotation))
+    res = model.fit_accumulate_test(samples, len_vec, float(opts.threshold), filename, int(opts.miter))
+    params_vec1, params_vec2, params_vecList, iter_id1, iter_id2, cost_vec, state_vec = res
+    mdict = {'state_vec': state_vec, 'len_vec': np.asarray(len_vec), 'params_vec1': params_vec1,
+             'params_vec2': params_vec2, 'iter_id1': iter_id1, 'iter_id2': iter_id2, 'cost_vec': cost_vec}
+    os.makedirs(output_path, exist_ok=True)
+    scipy.io.savemat("%s/estimate_ou_%d_%.2f_%d.mat" % (output_path, run_id, cons_param, K), mdict)
+    model.close()
+    return mdict
+
+
+if __name__ == '__main__':
+    run(parse_args())

@@ -342,6 +342,23 @@ def make_ou_cases():
     print("wrote ou_cases")
 
 
+def make_cli_defaults():
+    """The reference's own parse_args() (phylo_hmrf.py:1531-1568) on an empty command line."""
+    import json
+    from optparse import OptionParser
+    g = {"OptionParser": OptionParser}
+    ref_loader.load_functions("phylo_hmrf.py", ["parse_args"], 0, g)
+    old = sys.argv
+    sys.argv = ["phylo_hmrf.py"]
+    try:
+        opts = g["parse_args"]()
+    finally:
+        sys.argv = old
+    with open(os.path.join(HERE, "cli_defaults.json"), "w") as f:
+        json.dump(vars(opts), f, indent=1, sort_keys=True)
+    print("wrote cli_defaults", len(vars(opts)))
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present; fixtures can only be regenerated in the build container")
@@ -354,6 +371,7 @@ def main():
     make_edge_cases()
     make_fit_driver_cases()
     make_ou_cases()
+    make_cli_defaults()
 
 
 if __name__ == "__main__":
