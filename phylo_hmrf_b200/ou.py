@@ -122,6 +122,10 @@ def _regularised_logdet_trace(V, S, weight, min_covar, logdet_eps):
     add min_covar*I up to 10 times while cond(V) >= 1/eps_machine, then fall back to the
     pseudo-inverse (:1115-1131).  Returns (value, V actually used)."""
     d = V.shape[-1]
+    if not (np.all(np.isfinite(V)) and np.all(np.isfinite(S))):
+        # the optimiser wandered to non-finite parameters: LAPACK's SVD would spin (or raise) on
+        # them; report an unusable point instead (the reference crashes here)
+        return np.inf, V
     for _ in range(11):
         if np.linalg.cond(V) < 1 / sys.float_info.epsilon:
             return weight * np.log(np.linalg.det(V) + logdet_eps) + np.sum(np.linalg.inv(V) * S), V
@@ -159,7 +163,10 @@ def mstep_objective_batch(tree, params, stats, n_samples, lambda_0, min_covar):
     obsmean = stats['obs'][:, :, None] * mu[:, None, :]
     Sn_w = (stats['obs*obs.T'] - obsmean - obsmean.transpose(0, 2, 1)
             + mu[:, :, None] * mu[:, None, :] * stats['post'][:, None, None])
-    good = np.linalg.cond(V) < 1 / sys.float_info.epsilon
+    finite = np.all(np.isfinite(V), axis=(1, 2)) & np.all(np.isfinite(Sn_w), axis=(1, 2))
+    good = np.zeros(K, dtype=bool)
+    if finite.any():
+        good[finite] = np.linalg.cond(V[finite]) < 1 / sys.float_info.epsilon
     core = np.empty(K)
     if good.any():
         Vg = V[good]
@@ -183,6 +190,8 @@ def single_objective(tree, params, obs, min_covar):
     Sn_w = np.dot(obs.T, obs) / n - obsmean - obsmean.T + np.outer(mu, mu)
     Vt = V
     lik = np.nan
+    if not (np.all(np.isfinite(V)) and np.all(np.isfinite(Sn_w))):
+        return np.inf, values, V
     for _ in range(11):
         if np.linalg.cond(Vt) < 1 / sys.float_info.epsilon:
             lik = np.log(np.linalg.det(Vt)) + np.sum(np.linalg.inv(Vt) * Sn_w)
@@ -228,8 +237,11 @@ def fit_cluster(tree, obs, mean_values, magnitude, min_covar, rng):
     params = None
     for _ in range(11):
         guess = init_guess(tree, mean_values, magnitude, rng)
-        res = minimize(lambda p: single_objective(tree, p, obs, min_covar)[0], guess, constraints=_BOX, tol=1e-6,
-                       options={'disp': False})
+        try:
+            res = minimize(lambda p: single_objective(tree, p, obs, min_covar)[0], guess, constraints=_BOX, tol=1e-6,
+                           options={'disp': False})
+        except Exception:
+            continue
         params = res.x
         if tree.check_params(params) > 0:
             return params, single_objective(tree, params, obs, min_covar)[0]
