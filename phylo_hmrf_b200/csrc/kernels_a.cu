@@ -265,41 +265,42 @@ __device__ __forceinline__ double div_by_dwf(double u, double dwf, double y) {
     return __fma_rn(r1, y, q1);
 }
 
-template <int TN>
+// One warp owns 32 consecutive nodes: it reads their K log-likelihood rows (256 B each,
+// coalesced), converts, stages the 32 x K integers in its own shared-memory tile and streams
+// them out as one contiguous 128*K-byte run.  No block-wide barrier: the warps of a CTA are
+// independent, so loads of one overlap stores of another.
 __global__ void __launch_bounds__(256) quantise_unary_kernel(const double *__restrict__ logp, int64_t n, int64_t ld,
                                                               int K, const double *__restrict__ dwf_dev, double tol,
                                                               int32_t *__restrict__ unary,
                                                               long long *__restrict__ blist, long long bcap,
                                                               unsigned long long *bcount) {
-    extern __shared__ int32_t tile[];  // [TN][K]
+    extern __shared__ __align__(16) int32_t tile_all[];  // [warps][32][K]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t *tile = tile_all + (size_t)warp * 32 * K;
     const double dwf = dwf_dev[0];
     const double ydwf = 1.0 / dwf;  // IEEE division: the correctly rounded reciprocal
     // the refinement needs a finite, normal reciprocal; otherwise use the plain division
     const bool fast_div = (dwf > 1e-290) && (dwf < 1e290);
-    const int lane_n = threadIdx.x % TN;
-    const int kgrp = threadIdx.x / TN;
-    constexpr int KG = 256 / TN;
-    constexpr int U = 4;  // states in flight per thread
-    const int64_t n_tiles = (n + TN - 1) / TN;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t base = t * TN;
-        const int64_t i = base + lane_n;
-        const int cnt = (int)((n - base) < TN ? (n - base) : TN);
+    constexpr int U = 6;  // states in flight per thread
+    const int64_t n_tiles = (n + 31) >> 5;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; t < n_tiles; t += wstride) {
+        const int64_t base = t << 5;
+        const int64_t i = base + lane;
+        const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
         if (i < n) {
-            for (int k0 = kgrp; k0 < K; k0 += KG * U) {
+            const double *src = logp + i;
+            for (int k0 = 0; k0 < K; k0 += U) {
                 double u[U];
 #pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    const int k = k0 + q * KG;
-                    u[q] = k < K ? -logp[k * ld + i] : 0.0;
-                }
+                for (int q = 0; q < U; ++q) u[q] = (k0 + q) < K ? -src[(int64_t)(k0 + q) * ld] : 0.0;
 #pragma unroll
                 for (int q = 0; q < U; ++q) {
-                    const int k = k0 + q * KG;
+                    const int k = k0 + q;
                     if (k < K) {
                         const double quo = fast_div ? div_by_dwf(u[q], dwf, ydwf) : __ddiv_rn(u[q], dwf);
                         const double tq = __dmul_rn(quo, 100000.0);
-                        tile[lane_n * K + k] = __double2int_rz(tq);
+                        tile[lane * K + k] = __double2int_rz(tq);
                         // |tq| <= 1e5: nearest integer through the 2^52+2^51 constant
                         const double r = (tq + 6755399441055744.0) - 6755399441055744.0;
                         const double dist = fabs(tq - r);
@@ -311,17 +312,17 @@ __global__ void __launch_bounds__(256) quantise_unary_kernel(const double *__res
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
         int32_t *dst = unary + base * K;
         const int total = cnt * K;
-        if ((total & 3) == 0) {
+        if ((total & 3) == 0) {  // base*K*4 is a multiple of 128 bytes
             const int4 *src4 = reinterpret_cast<const int4 *>(tile);
             int4 *dst4 = reinterpret_cast<int4 *>(dst);
-            for (int e = threadIdx.x; e < (total >> 2); e += 256) dst4[e] = src4[e];
+            for (int e = lane; e < (total >> 2); e += 32) dst4[e] = src4[e];
         } else {
-            for (int e = threadIdx.x; e < total; e += 256) dst[e] = tile[e];
+            for (int e = lane; e < total; e += 32) dst[e] = tile[e];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -330,27 +331,20 @@ int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, cons
                           int sm_count, cudaStream_t s) {
     PHMRF_CUDA(cudaMemsetAsync(bcount, 0, sizeof(unsigned long long), s));
     if (n == 0) return PHMRF_OK;
-    const size_t budget = 200 * 1024;
-    int tn = 128;
-    while (tn > 32 && (size_t)tn * K * 4 > 48 * 1024) tn >>= 1;
-    size_t smem = (size_t)tn * K * 4;
-    if (smem > budget) {
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 32 * K * 4 > 64 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 32 * K * 4;
+    if (smem > 200 * 1024) {
         set_error("n_states too large for the quantise tile");
         return PHMRF_E_UNSUPPORTED;
     }
-    int64_t n_tiles = (n + tn - 1) / tn;
-    int64_t cap = (int64_t)sm_count * 8;
-    int grid = (int)(n_tiles < cap ? n_tiles : cap);
-#define PHMRF_Q(TN)                                                                                          \
-    {                                                                                                        \
-        if (smem > 48 * 1024)                                                                                \
-            PHMRF_CUDA(cudaFuncSetAttribute(quantise_unary_kernel<TN>,                                       \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        quantise_unary_kernel<TN><<<grid, 256, smem, s>>>(logp, n, ld, K, dwf_dev, tol, unary, blist, bcap, \
-                                                          bcount);                                           \
-    }
-    if (tn == 128) PHMRF_Q(128) else if (tn == 64) PHMRF_Q(64) else PHMRF_Q(32)
-#undef PHMRF_Q
+    if (smem > 48 * 1024)
+        PHMRF_CUDA(cudaFuncSetAttribute(quantise_unary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (n + 31) / 32;
+    const int64_t blocks = (n_tiles + warps - 1) / warps;
+    const int64_t cap = (int64_t)sm_count * 6;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    quantise_unary_kernel<<<grid, warps * 32, smem, s>>>(logp, n, ld, K, dwf_dev, tol, unary, blist, bcap, bcount);
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     return PHMRF_OK;
