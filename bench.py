@@ -143,41 +143,49 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     seed = 20261017 + 5
-    g, (B, d, K, n_bands, r0, r1) = build_band(args.workload, rank, seed)
-    n = g["n_own"]
-    # model: identical on every rank (seeded from rank-0-independent data: the first rows)
+    B, d, K, n_bands = WORKLOADS[args.workload]
+    # model: identical on every rank (a pure function of the seed and the first rows of the map)
     g0 = synth.make_band(seed, B, d, 0, min(B, 24), beta1=BETA1)
     means, covars = synth.model(seed, g0["X_own"], K, d)
+    del g0
     V = synth.potts(K, BETA)
-
     stream = torch.cuda.Stream()
     m = ph.Model(K, d, device=local_rank)
     m.set_model(means, covars, V)
-    # pinned host buffers for the end-to-end leg
-    X_pin = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
-    X_pin.numpy()[:] = g["X_own"]
-    reg = m.region(X_pin.numpy(), g["edge_ids"], g["edge_w"], n_window=g["n_window"], own_offset=g["own_offset"],
-                   stream=stream.cuda_stream)
-    E = len(g["edge_ids"])
-    x_win = g["x"]
-    del g["X_window"], g["edge_dist"]
 
-    # labels for phase B: arg-min of the integer unary over the *window* (owned + halo rows);
-    # the halo labels come from a throw-away region over the window (what the neighbouring
-    # bands' graph cuts would have produced).
-    if g["n_window"] != n:
-        Xw = synth.features(seed, g["x"], g["y"], d)
-        win = m.region(Xw, np.zeros((0, 2), np.int64), np.zeros(0))
-        win.emit_loglik()
-        win.quantise(want_unary=False, want_edges=False)
-        labels_window = win.labels_argmin_unary()
-        win.close()
-        del Xw
-    else:
-        reg.emit_loglik()
-        reg.quantise(want_unary=False, want_edges=False)
-        labels_window = reg.labels_argmin_unary()
-    reg.set_labels(labels_window)
+    # Host-side input preparation peaks at ~15 GB per rank (edge lists in int64/float64 plus NumPy
+    # temporaries): let the ranks through two at a time so that an 8-rank run stays far below the
+    # box's RAM, and drop every temporary as soon as the region is resident on the device.
+    setup = {}
+    for turn in range(0, world, 2):
+        if turn <= rank < turn + 2:
+            g, (_, _, _, _, r0, r1) = build_band(args.workload, rank, seed)
+            n, n_window, E = g["n_own"], g["n_window"], len(g["edge_ids"])
+            X_pin = torch.empty((n, d), dtype=torch.float64, pin_memory=True)  # pinned: end-to-end leg
+            X_pin.numpy()[:] = g["X_own"]
+            reg = m.region(X_pin.numpy(), g["edge_ids"], g["edge_w"], n_window=n_window, own_offset=g["own_offset"],
+                           stream=stream.cuda_stream)
+            for key in ("edge_ids", "edge_w", "edge_dist", "x", "y", "X_own"):
+                g.pop(key, None)
+            # labels for phase B: arg-min of the integer unary over the *window* (owned + halo rows);
+            # the halo labels come from a throw-away region over the window (what the neighbouring
+            # bands' graph cuts would have produced)
+            if n_window != n:
+                win = m.region(g["X_window"], np.zeros((0, 2), np.int64), np.zeros(0))
+                win.emit_loglik()
+                win.quantise(want_unary=False, want_edges=False)
+                labels_window = win.labels_argmin_unary()
+                win.close()
+            else:
+                reg.emit_loglik()
+                reg.quantise(want_unary=False, want_edges=False)
+                labels_window = reg.labels_argmin_unary()
+            reg.set_labels(labels_window)
+            g.clear()
+            setup = dict(n=n, n_window=n_window, E=E, r0=r0, r1=r1)
+        if world > 1:
+            dist.barrier()
+    n, n_window, E, r0, r1 = (setup[k] for k in ("n", "n_window", "E", "r0", "r1"))
 
     stats_len = m.stats_len
 
@@ -252,7 +260,7 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     unary_pin = torch.empty((n, K), dtype=torch.int32, pin_memory=True)
     wi_pin = torch.empty(E, dtype=torch.int32, pin_memory=True)
-    lab_pin = torch.empty(g["n_window"], dtype=torch.int32, pin_memory=True)
+    lab_pin = torch.empty(n_window, dtype=torch.int32, pin_memory=True)
     lab_pin.numpy()[:] = labels_window
     lib = ph._lib.lib()
     import ctypes as C
@@ -288,7 +296,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    h2d = n * d * 8 + g["n_window"] * 4
+    h2d = n * d * 8 + n_window * 4
     d2h = n * K * 4 + E * 4 + stats_len * 8
 
     if rank != 0:
