@@ -370,6 +370,11 @@ def _cpu_region(args):
     seed, B, d, K = args
     from phylo_hmrf_b200 import synth
     from oracle import phmrf_oracle as orc
+    try:  # one BLAS/OpenMP thread per region process: the processes already fill the cores
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     g = synth.make_band(seed, B, d, beta1=BETA1)
     g0 = synth.make_band(20261017 + 5, 24895 if d == 9 else 4979, d, 0, 24, beta1=BETA1)
     means, covars = synth.model(20261017 + 5, g0["X_own"], K, d)
@@ -397,7 +402,7 @@ def cpu_sample(d, K, B_crop, n_regions, pool=None):
 
 
 def cpu_baseline(d, K, seconds=15.0):
-    cores = min(os.cpu_count() or 1, 8)
+    cores = min(os.cpu_count() or 1, 32)
     B_crop = 60
     nodes, wall, inner = cpu_sample(d, K, B_crop, cores)
     reps = max(1, int(seconds / max(wall, 1e-3)) - 1)
@@ -416,7 +421,7 @@ def run_reference(args):
     if rank != 0:
         return
     B, d, K, _ = WORKLOADS[args.workload]
-    cores = min(os.cpu_count() or 1, 8)
+    cores = min(os.cpu_count() or 1, 32)
     B_crop = 60
     for _ in range(min(args.warmup, 1)):
         cpu_sample(d, K, B_crop, cores)
