@@ -167,6 +167,20 @@ int64_t phmrf_grid_edge_count(int kind, int64_t n1, int64_t n2, int num_neighbor
 int phmrf_grid_edges(int device, const double *X, int n_features, int kind, int64_t n1, int64_t n2, int num_neighbor,
                      double *edge_list_out, int64_t n_edges);
 
+/* A region -- or the row band [row0,row1) of one -- built entirely on the device from the
+ * grid geometry: X_window holds the features of rows [max(row0-1,0), min(row1+1,rows)) in the
+ * region's node order; the 8-/4-neighbour graph, d_ij, w = exp(-beta1*d_ij) (phylo_hmrf.py:585)
+ * and the neighbour slots are computed by kernels, so no edge array crosses PCIe.  The edge list
+ * (window-local ids, sorted by (id1,id2); every edge incident to an owned node) can be read back
+ * for the host graph cut with phmrf_region_edges. */
+int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, int64_t n1, int64_t n2, int64_t row0,
+                             int64_t row1, int num_neighbor, double beta1, void *stream, phmrf_region **out);
+int64_t phmrf_region_n_edges(const phmrf_region *r);
+int64_t phmrf_region_n_own(const phmrf_region *r);
+int64_t phmrf_region_n_window(const phmrf_region *r);
+int64_t phmrf_region_own_offset(const phmrf_region *r);
+int phmrf_region_edges(phmrf_region *r, int64_t *edge_ids_out, double *edge_w_out);
+
 /* ------------------------------------------------------------------ probes ------------ */
 
 /* FP64 FMA-pipe peak of the current device, measured with a dependent-chain DFMA

@@ -60,6 +60,13 @@ SIGNATURES = {
     "phmrf_quantise_async": (C.c_int, [_vp, C.c_double, C.c_double]),
     "phmrf_estep_stats_async": (C.c_int, [_vp, C.c_int]),
     "phmrf_launch_count": (C.c_int64, []),
+    "phmrf_region_create_grid": (C.c_int, [_vp, _c_double_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                           C.c_double, _vp, C.POINTER(_vp)]),
+    "phmrf_region_n_edges": (C.c_int64, [_vp]),
+    "phmrf_region_n_own": (C.c_int64, [_vp]),
+    "phmrf_region_n_window": (C.c_int64, [_vp]),
+    "phmrf_region_own_offset": (C.c_int64, [_vp]),
+    "phmrf_region_edges": (C.c_int, [_vp, _c_int64_p, _c_double_p]),
     "phmrf_grid_edge_count": (C.c_int64, [C.c_int, C.c_int64, C.c_int64, C.c_int]),
     "phmrf_grid_edges": (C.c_int, [C.c_int, _c_double_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _c_double_p,
                                    C.c_int64]),

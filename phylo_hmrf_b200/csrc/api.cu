@@ -55,6 +55,7 @@ struct phmrf_region {
     double *d_nbr_w = nullptr;   // [W][ld]
     double *d_edge_w = nullptr;  // [E]
     int32_t *d_edge_wi = nullptr;
+    long long *d_edge_ids = nullptr;  // [E,2] window-local, only for regions built by phmrf_region_create_grid
     unsigned long long *d_absmax = nullptr;  // [1] bits, [1] boundary counter
     double *d_dwf = nullptr;                 // [2] dwf, absmax
     long long *d_blist = nullptr;
@@ -360,6 +361,123 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
     return PHMRF_OK;
 }
 
+int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, int64_t n1, int64_t n2, int64_t row0,
+                             int64_t row1, int num_neighbor, double beta1, void *stream, phmrf_region **out) {
+    const int64_t rows = kind == 1 ? n2 : n1;
+    if (!ctx || !out || !X_window || (kind != 0 && kind != 1) || n1 < 1 || n2 < 1 || (kind == 1 && n1 != n2) ||
+        (num_neighbor != 8 && num_neighbor != 4) || row0 < 0 || row1 <= row0 || row1 > rows) {
+        set_error("phmrf_region_create_grid: invalid geometry (kind 0/1, num_neighbor 8/4, 0 <= row0 < row1 <= rows)");
+        return PHMRF_E_INVALID;
+    }
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    const int K = ctx->K, D = ctx->D;
+    const int64_t h0 = row0 > 0 ? row0 - 1 : 0, h1 = row1 < rows ? row1 + 1 : rows;
+    const int64_t win_start = grid_row_start(kind, n1, n2, h0), win_end = grid_row_start(kind, n1, n2, h1);
+    const int64_t own_start = grid_row_start(kind, n1, n2, row0), own_end = grid_row_start(kind, n1, n2, row1);
+    const int64_t n_window = win_end - win_start, n_own = own_end - own_start;
+    if (n_window >= ((int64_t)1 << 31)) {
+        set_error("phmrf_region_create_grid: window too large for 32-bit neighbour ids");
+        return PHMRF_E_INVALID;
+    }
+    phmrf_region *r = new phmrf_region();
+    r->ctx = ctx;
+    r->n = n_own;
+    r->n_window = n_window;
+    r->own_offset = own_start - win_start;
+    r->W = num_neighbor;
+    r->ld = round_up(n_own > 0 ? n_own : 1, 64);
+    if (stream) {
+        r->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete r;
+            return cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__);
+        }
+        r->own_stream = true;
+    }
+    const int64_t ld = r->ld;
+    const int F = n_stat_features(D);
+    double *dXw = nullptr;
+#define TRY(x)                     \
+    if ((rc = (x)) != PHMRF_OK) {  \
+        cudaFree(dXw);             \
+        phmrf_region_destroy(r);   \
+        return rc;                 \
+    }
+    if (cudaMalloc((void **)&dXw, sizeof(double) * n_window * D) != cudaSuccess ||
+        cudaMemcpyAsync(dXw, X_window, sizeof(double) * n_window * D, cudaMemcpyHostToDevice, r->stream) !=
+            cudaSuccess) {
+        cudaError_t err = cudaGetLastError();
+        cudaFree(dXw);
+        phmrf_region_destroy(r);
+        return cuda_fail(err, "upload X window", __FILE__, __LINE__);
+    }
+    long long n_edges = 0;
+    TRY(dev_alloc(r, &r->d_absmax, 2));
+    TRY(launch_band_graph(dXw, kind, n1, n2, num_neighbor, D, win_start, own_start, own_end, n_window, beta1, ld,
+                          nullptr, nullptr, nullptr, nullptr, &n_edges, nullptr, r->stream));
+    r->E = n_edges;
+    TRY(dev_alloc(r, &r->d_X, (int64_t)D * ld));
+    TRY(dev_alloc(r, &r->d_logp, (int64_t)K * ld));
+    TRY(dev_alloc(r, &r->d_unary, n_own * K));
+    TRY(dev_alloc(r, &r->d_labels, n_window));
+    TRY(dev_alloc(r, &r->d_nbr_id, (int64_t)r->W * ld));
+    TRY(dev_alloc(r, &r->d_nbr_w, (int64_t)r->W * ld));
+    TRY(dev_alloc(r, &r->d_edge_w, n_edges));
+    TRY(dev_alloc(r, &r->d_edge_wi, n_edges));
+    TRY(dev_alloc(r, &r->d_edge_ids, 2 * n_edges));
+    TRY(dev_alloc(r, &r->d_dwf, 2));
+    r->bcap = 1 << 20;
+    TRY(dev_alloc(r, &r->d_blist, r->bcap));
+    TRY(dev_alloc(r, &r->d_partials, (int64_t)ctx->sm_count * ((int64_t)K * F + 3)));
+    TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
+    TRY(dev_alloc(r, &r->d_flags, 1));
+    if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess) {
+        cudaError_t err = cudaGetLastError();
+        cudaFree(dXw);
+        phmrf_region_destroy(r);
+        return cuda_fail(err, "memset X", __FILE__, __LINE__);
+    }
+    TRY(launch_aos_to_soa(dXw + r->own_offset * D, r->d_X, n_own, D, ld, r->stream));
+    // max|w| lands in d_absmax[1] (free until the first quantise resets it as the boundary counter)
+    TRY(launch_band_graph(dXw, kind, n1, n2, num_neighbor, D, win_start, own_start, own_end, n_window, beta1, ld,
+                          r->d_nbr_id, r->d_nbr_w, r->d_edge_ids, r->d_edge_w, &n_edges, r->d_absmax + 1, r->stream));
+    unsigned long long wbits = 0;
+    if (cudaMemcpy(&wbits, r->d_absmax + 1, sizeof(wbits), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaError_t err = cudaGetLastError();
+        cudaFree(dXw);
+        phmrf_region_destroy(r);
+        return cuda_fail(err, "read max|w|", __FILE__, __LINE__);
+    }
+    std::memcpy(&r->wmax, &wbits, sizeof(double));
+#undef TRY
+    cudaFree(dXw);
+    *out = r;
+    return PHMRF_OK;
+}
+
+int64_t phmrf_region_n_edges(const phmrf_region *r) { return r ? r->E : 0; }
+int64_t phmrf_region_n_own(const phmrf_region *r) { return r ? r->n : 0; }
+int64_t phmrf_region_n_window(const phmrf_region *r) { return r ? r->n_window : 0; }
+int64_t phmrf_region_own_offset(const phmrf_region *r) { return r ? r->own_offset : 0; }
+
+int phmrf_region_edges(phmrf_region *r, int64_t *edge_ids_out, double *edge_w_out) {
+    if (!r) return PHMRF_E_INVALID;
+    if (!r->d_edge_ids) {
+        set_error("phmrf_region_edges: only regions built by phmrf_region_create_grid keep their edge list");
+        return PHMRF_E_STATE;
+    }
+    int rc = set_device(r->ctx);
+    if (rc) return rc;
+    if (r->E > 0) {
+        if (edge_ids_out)
+            PHMRF_CUDA(cudaMemcpy(edge_ids_out, r->d_edge_ids, sizeof(long long) * 2 * r->E, cudaMemcpyDeviceToHost));
+        if (edge_w_out) PHMRF_CUDA(cudaMemcpy(edge_w_out, r->d_edge_w, sizeof(double) * r->E, cudaMemcpyDeviceToHost));
+    }
+    return PHMRF_OK;
+}
+
 int phmrf_region_update_X(phmrf_region *r, const double *X) {
     if (!r || (!X && r->n > 0)) return PHMRF_E_INVALID;
     int rc = set_device(r->ctx);
@@ -386,6 +504,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     cudaFree(r->d_nbr_w);
     cudaFree(r->d_edge_w);
     cudaFree(r->d_edge_wi);
+    cudaFree(r->d_edge_ids);
     cudaFree(r->d_absmax);
     cudaFree(r->d_dwf);
     cudaFree(r->d_blist);

@@ -85,6 +85,12 @@ long long grid_edge_count(int kind, long long n1, long long n2, int nn);
 int launch_grid_edges(const double *X_dev, int kind, long long n1, long long n2, int nn, int D, long long n,
                       long long n_edges, double *edge_list_dev, cudaStream_t s);
 
+long long grid_row_start(int kind, long long n1, long long n2, long long row);
+int launch_band_graph(const double *Xw_dev, int kind, long long n1, long long n2, int nn, int D, long long win_start,
+                      long long own_start, long long own_end, long long n_window, double beta1, long long ld,
+                      int32_t *nbr_id, double *nbr_w, long long *ids_dev, double *w_dev, long long *n_edges,
+                      unsigned long long *wmax_bits, cudaStream_t s);
+
 // ---- probes (probe.cu) ----------------------------------------------------------------
 int run_probe(int which, double *out);
 

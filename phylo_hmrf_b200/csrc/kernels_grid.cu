@@ -119,6 +119,104 @@ __global__ void grid_fill_kernel(Grid g, long long n, int D, const double *__res
     }
 }
 
+// ---- a row band of a region, built entirely on the device ------------------------------
+struct Band {
+    long long win_start, own_start, own_end;  // global node ids: window [win_start, ...), owned [own_start, own_end)
+};
+
+__device__ __forceinline__ double edge_distance(const double *xi, const double *xj, int D, bool halve) {
+    double ni = 0.0, nj = 0.0, dd = 0.0;
+    for (int j = 0; j < D; ++j) {
+        ni = fma(xi[j], xi[j], ni);
+        nj = fma(xj[j], xj[j], nj);
+        const double t = xi[j] - xj[j];
+        dd = fma(t, t, dd);
+    }
+    double w = dd / (sqrt(ni) * sqrt(nj) + 1e-16);
+    return halve ? 0.5 * w : w;
+}
+
+__device__ __forceinline__ bool owned(const Band &b, long long id) { return id >= b.own_start && id < b.own_end; }
+
+__global__ void band_count_kernel(Grid g, Band b, long long n_window, int *__restrict__ counts) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_window;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = b.win_start + t;
+        long long x, y, nid[4];
+        bool bd[4];
+        node_xy(g, i, x, y);
+        const int c = forward_neighbours(g, x, y, nid, bd);
+        int kept = 0;
+        for (int e = 0; e < c; ++e) kept += (owned(b, i) || owned(b, nid[e])) ? 1 : 0;
+        counts[t] = kept;
+    }
+}
+
+// edge list of the band in (id1,id2) order: window-local ids, w = exp(-beta1 * d_ij)
+__global__ void band_fill_kernel(Grid g, Band b, long long n_window, int D, const double *__restrict__ Xw,
+                                 double beta1, const long long *__restrict__ offsets, long long *__restrict__ ids,
+                                 double *__restrict__ w_out, unsigned long long *wmax_bits) {
+    unsigned long long wmax = 0ull;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_window;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = b.win_start + t;
+        long long x, y, nid[4];
+        bool bd[4];
+        node_xy(g, i, x, y);
+        const int c = forward_neighbours(g, x, y, nid, bd);
+        long long pos = offsets[t];
+        for (int e = 0; e < c; ++e) {
+            if (owned(b, i) || owned(b, nid[e])) {
+                const double w = exp(-beta1 * edge_distance(Xw + t * D, Xw + (nid[e] - b.win_start) * D, D, bd[e]));
+                ids[2 * pos] = t;
+                ids[2 * pos + 1] = nid[e] - b.win_start;
+                w_out[pos] = w;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(w));
+                wmax = bits > wmax ? bits : wmax;
+                ++pos;
+            }
+        }
+    }
+    if (wmax) atomicMax(wmax_bits, wmax);
+}
+
+// neighbour slots of every owned node in ascending neighbour id (the order in which the
+// host builder meets the incident edges of a sorted edge list)
+__global__ void band_ell_kernel(Grid g, Band b, long long n_own, long long ld, int D, const double *__restrict__ Xw,
+                                double beta1, int W, int32_t *__restrict__ nbr_id, double *__restrict__ nbr_w) {
+    const bool tri = g.kind != 0;
+    const long long rows = tri ? g.n2 : g.n1, cols = g.n2;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n_own;
+         o += (long long)gridDim.x * blockDim.x) {
+        const long long i = b.own_start + o;
+        long long x, y;
+        node_xy(g, i, x, y);
+        const double *xi = Xw + (i - b.win_start) * D;
+        int s = 0;
+        auto put = [&](long long a, long long c2) {
+            if (a >= 0 && a < rows && c2 >= 0 && c2 < cols && (!tri || a <= c2)) {
+                const long long j = node_id(g, a, c2);
+                const bool halve = tri && x == y && a == c2;
+                nbr_id[s * ld + o] = (int32_t)(j - b.win_start);
+                nbr_w[s * ld + o] = exp(-beta1 * edge_distance(xi, Xw + (j - b.win_start) * D, D, halve));
+                ++s;
+            }
+        };
+        if (g.nn == 8) put(x - 1, y - 1);
+        put(x - 1, y);
+        if (g.nn == 8) put(x - 1, y + 1);
+        put(x, y - 1);
+        put(x, y + 1);
+        if (g.nn == 8) put(x + 1, y - 1);
+        put(x + 1, y);
+        if (g.nn == 8) put(x + 1, y + 1);
+        for (; s < W; ++s) {
+            nbr_id[s * ld + o] = -1;
+            nbr_w[s * ld + o] = 0.0;
+        }
+    }
+}
+
 }  // namespace
 
 // Closed-form edge count of a dense region.
@@ -158,6 +256,73 @@ int launch_grid_edges(const double *X_dev, int kind, long long n1, long long n2,
     cudaFree(tmp);
     (void)n_edges;
     if (e != cudaSuccess) return cuda_fail(e, "grid edge kernels", __FILE__, __LINE__);
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+long long grid_row_start(int kind, long long n1, long long n2, long long row) {
+    (void)n1;
+    return kind == 0 ? row * n2 : row * n2 - (row * (row - 1)) / 2;
+}
+
+// Builds, for the band of rows [row0,row1) of a region whose window features Xw_dev ([n_window,D],
+// row-major) are on the device: the edge list (ids window-local, weights), and the ELL slots.
+// ids_dev / w_dev may be nullptr for a counting call (returns the edge count in *n_edges).
+int launch_band_graph(const double *Xw_dev, int kind, long long n1, long long n2, int nn, int D, long long win_start,
+                      long long own_start, long long own_end, long long n_window, double beta1, long long ld,
+                      int32_t *nbr_id, double *nbr_w, long long *ids_dev, double *w_dev, long long *n_edges,
+                      unsigned long long *wmax_bits, cudaStream_t s) {
+    Grid g{kind, n1, n2, nn};
+    Band b{win_start, own_start, own_end};
+    const long long n_own = own_end - own_start;
+    const int grid = (int)((n_window + 255) / 256 < 148 * 16 ? (n_window + 255) / 256 : 148 * 16);
+    if (ids_dev == nullptr) {
+        int *counts = nullptr;
+        long long *offsets = nullptr;
+        void *tmp = nullptr;
+        size_t tmp_bytes = 0;
+        PHMRF_CUDA(cudaMalloc((void **)&counts, sizeof(int) * (n_window + 1)));
+        PHMRF_CUDA(cudaMalloc((void **)&offsets, sizeof(long long) * (n_window + 1)));
+        PHMRF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (n_window + 1), s));
+        band_count_kernel<<<grid, 256, 0, s>>>(g, b, n_window, counts);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offsets, n_window + 1, s);
+        PHMRF_CUDA(cudaMalloc(&tmp, tmp_bytes));
+        cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offsets, n_window + 1, s);
+        count_launch(2);
+        long long total = 0;
+        PHMRF_CUDA(cudaMemcpyAsync(&total, offsets + n_window, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        PHMRF_CUDA(cudaStreamSynchronize(s));
+        *n_edges = total;
+        // keep the offsets for the fill call: stash them behind the caller's back is not possible
+        // with plain pointers, so the fill call recomputes them (two cheap kernels)
+        cudaFree(counts);
+        cudaFree(offsets);
+        cudaFree(tmp);
+        return PHMRF_OK;
+    }
+    int *counts = nullptr;
+    long long *offsets = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    PHMRF_CUDA(cudaMalloc((void **)&counts, sizeof(int) * (n_window + 1)));
+    PHMRF_CUDA(cudaMalloc((void **)&offsets, sizeof(long long) * (n_window + 1)));
+    PHMRF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (n_window + 1), s));
+    band_count_kernel<<<grid, 256, 0, s>>>(g, b, n_window, counts);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offsets, n_window + 1, s);
+    PHMRF_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offsets, n_window + 1, s);
+    PHMRF_CUDA(cudaMemsetAsync(wmax_bits, 0, sizeof(unsigned long long), s));
+    band_fill_kernel<<<grid, 256, 0, s>>>(g, b, n_window, D, Xw_dev, beta1, offsets, ids_dev, w_dev, wmax_bits);
+    if (n_own > 0) {
+        const int grid2 = (int)((n_own + 255) / 256 < 148 * 16 ? (n_own + 255) / 256 : 148 * 16);
+        band_ell_kernel<<<grid2, 256, 0, s>>>(g, b, n_own, ld, D, Xw_dev, beta1, nn, nbr_id, nbr_w);
+    }
+    count_launch(4);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(counts);
+    cudaFree(offsets);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "band graph kernels", __FILE__, __LINE__);
     PHMRF_CUDA(cudaGetLastError());
     return PHMRF_OK;
 }

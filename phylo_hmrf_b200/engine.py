@@ -38,6 +38,11 @@ class Model:
     def region(self, X, edge_ids, edge_w, n_window=None, own_offset=0, stream=None):
         return Region(self, X, edge_ids, edge_w, n_window, own_offset, stream)
 
+    def region_grid(self, X_window, kind, n1, n2, row0=0, row1=None, num_neighbor=8, beta1=0.5, stream=None):
+        """Region (or row band [row0,row1)) built on the device from the grid geometry; see
+        phmrf_region_create_grid.  kind: 1 diagonal region (n1 == n2 bins), 0 rectangle."""
+        return GridRegion(self, X_window, kind, n1, n2, row0, row1, num_neighbor, beta1, stream)
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().phmrf_ctx_destroy(self._h)
@@ -179,6 +184,40 @@ class Region:
             self.close()
         except Exception:
             pass
+
+
+class GridRegion(Region):
+    """A region whose graph was built by kernels from the grid geometry."""
+
+    def __init__(self, model, X_window, kind, n1, n2, row0, row1, num_neighbor, beta1, stream=None):
+        X = as_f64(X_window)
+        rows = n2 if kind == 1 else n1
+        row1 = rows if row1 is None else row1
+
+        def start(row):  # first node of a row in the region's node order
+            return row * n2 if kind == 0 else row * n2 - (row * (row - 1)) // 2
+
+        expect = start(min(row1 + 1, rows)) - start(max(row0 - 1, 0))
+        if X.ndim != 2 or X.shape != (expect, model.d):
+            raise ValueError("X_window must be [%d, %d]: rows [row0-1, row1+1) of the region" % (expect, model.d))
+        self.model = model
+        h = C.c_void_p()
+        check(_lib.lib().phmrf_region_create_grid(model._h, dptr(X), int(kind), int(n1), int(n2), int(row0), int(row1),
+                                                  int(num_neighbor), float(beta1), C.c_void_p(stream) if stream else None,
+                                                  C.byref(h)))
+        self._h = h
+        L = _lib.lib()
+        self.n = int(L.phmrf_region_n_own(h))
+        self.n_window = int(L.phmrf_region_n_window(h))
+        self.own_offset = int(L.phmrf_region_own_offset(h))
+        self.n_edges = int(L.phmrf_region_n_edges(h))
+
+    def edges(self):
+        """-> (edge_ids [E,2] int64 window-local, edge_w [E]) for the host graph cut."""
+        ids = np.empty((self.n_edges, 2), dtype=np.int64)
+        w = np.empty(self.n_edges, dtype=np.float64)
+        check(_lib.lib().phmrf_region_edges(self._h, i64ptr(ids), dptr(w)))
+        return ids, w
 
 
 def unpack_stats(flat, K, d):
