@@ -119,15 +119,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_band(workload, rank, seed):
-    from phylo_hmrf_b200 import synth
-    B, d, K, n_bands = WORKLOADS[workload]
-    rows = synth.band_rows(B, n_bands)
-    r0, r1 = rows[rank % n_bands]
-    g = synth.make_band(seed, B, d, r0, r1, beta1=BETA1)
-    return g, (B, d, K, n_bands, r0, r1)
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -153,39 +144,32 @@ def run_ours(args):
     m = ph.Model(K, d, device=local_rank)
     m.set_model(means, covars, V)
 
-    # Host-side input preparation peaks at ~15 GB per rank (edge lists in int64/float64 plus NumPy
-    # temporaries): let the ranks through two at a time so that an 8-rank run stays far below the
-    # box's RAM, and drop every temporary as soon as the region is resident on the device.
-    setup = {}
-    for turn in range(0, world, 2):
-        if turn <= rank < turn + 2:
-            g, (_, _, _, _, r0, r1) = build_band(args.workload, rank, seed)
-            n, n_window, E = g["n_own"], g["n_window"], len(g["edge_ids"])
-            X_pin = torch.empty((n, d), dtype=torch.float64, pin_memory=True)  # pinned: end-to-end leg
-            X_pin.numpy()[:] = g["X_own"]
-            reg = m.region(X_pin.numpy(), g["edge_ids"], g["edge_w"], n_window=n_window, own_offset=g["own_offset"],
-                           stream=stream.cuda_stream)
-            for key in ("edge_ids", "edge_w", "edge_dist", "x", "y", "X_own"):
-                g.pop(key, None)
-            # labels for phase B: arg-min of the integer unary over the *window* (owned + halo rows);
-            # the halo labels come from a throw-away region over the window (what the neighbouring
-            # bands' graph cuts would have produced)
-            if n_window != n:
-                win = m.region(g["X_window"], np.zeros((0, 2), np.int64), np.zeros(0))
-                win.emit_loglik()
-                win.quantise(want_unary=False, want_edges=False)
-                labels_window = win.labels_argmin_unary()
-                win.close()
-            else:
-                reg.emit_loglik()
-                reg.quantise(want_unary=False, want_edges=False)
-                labels_window = reg.labels_argmin_unary()
-            reg.set_labels(labels_window)
-            g.clear()
-            setup = dict(n=n, n_window=n_window, E=E, r0=r0, r1=r1)
-        if world > 1:
-            dist.barrier()
-    n, n_window, E, r0, r1 = (setup[k] for k in ("n", "n_window", "E", "r0", "r1"))
+    # The band is built on the device from the grid geometry (phmrf_region_create_grid): the host
+    # only prepares the window's feature rows, no edge array exists on the host or crosses PCIe.
+    r0, r1 = synth.band_rows(B, n_bands)[rank % n_bands]
+    g = synth.window_xy(B, r0, r1)
+    n, n_window, own_offset = g["n_own"], g["n_window"], g["own_offset"]
+    X_window = synth.features(seed, g["x"], g["y"], d)
+    g.clear()
+    reg = m.region_grid(X_window, 1, B, B, r0, r1, 8, BETA1, stream=stream.cuda_stream)
+    E = reg.n_edges
+    X_pin = torch.empty((n, d), dtype=torch.float64, pin_memory=True)  # pinned: end-to-end leg
+    X_pin.numpy()[:] = X_window[own_offset:own_offset + n]
+    # labels for phase B: arg-min of the integer unary over the *window* (owned + halo rows); the
+    # halo labels come from a throw-away region over the window (what the neighbouring bands' graph
+    # cuts would have produced)
+    if n_window != n:
+        win = m.region(X_window, np.zeros((0, 2), np.int64), np.zeros(0))
+        win.emit_loglik()
+        win.quantise(want_unary=False, want_edges=False)
+        labels_window = win.labels_argmin_unary()
+        win.close()
+    else:
+        reg.emit_loglik()
+        reg.quantise(want_unary=False, want_edges=False)
+        labels_window = reg.labels_argmin_unary()
+    reg.set_labels(labels_window)
+    del X_window
 
     stats_len = m.stats_len
 

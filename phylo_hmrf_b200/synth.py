@@ -35,6 +35,22 @@ def band_rows(B, n_bands):
     return [(cuts[i], cuts[i + 1]) for i in range(n_bands)]
 
 
+def window_xy(B, r0=0, r1=None):
+    """Coordinates of the window nodes (rows [r0-1, r1+1) clipped) of a band, without any edge
+    array: what `Model.region_grid` needs besides the features."""
+    r1 = B if r1 is None else r1
+    h0, h1 = max(r0 - 1, 0), min(r1 + 1, B)
+    rows = np.arange(h0, h1, dtype=np.int64)
+    lens = B - rows
+    x = np.repeat(rows, lens)
+    win_start = int(tri_row_start(B, h0))
+    n_window = int(tri_row_start(B, h1)) - win_start
+    y = np.arange(n_window, dtype=np.int64) - np.repeat(tri_row_start(B, rows) - win_start, lens) + x
+    own_start, own_end = int(tri_row_start(B, r0)), int(tri_row_start(B, r1))
+    return dict(B=B, r0=r0, r1=r1, x=x, y=y, n_window=n_window, n_own=own_end - own_start,
+                own_offset=own_start - win_start, win_start=win_start)
+
+
 def triangle_band(B, r0=0, r1=None):
     """Nodes and edges of rows [r0,r1) of a B-bin diagonal region with a one-row halo.
 
