@@ -66,14 +66,12 @@ struct EstepArgs {
     int D, K, W, estimate_type;
     double *post_soa;         // nullable [K][ld]
     double *pp_soa;           // nullable [K][ld] pairwise potential (signature-parity output)
-    double *partials;         // [grid][K*F + 4] per-block partial sums
+    double *partials;         // [sm_count][K*F + 3] per-CTA partial sums
     double *stats_out;        // [K*(1+D+D*D) + 3]
     int *flags;               // [1] device flag: bit 0 = the pipeline met an overflow, rerun on the general path
     int force_general;        // skip the pipeline kernel
     double s_bound;           // upper bound of any neighbour weight sum: beta * W * max|w|
 };
-// Returns the grid size it will use (for sizing `partials`) when args == nullptr.
-int estep_grid(int D, int K, int sm_count);
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s);
 // Warp-specialised pipeline (kernels_b2.cu); *handled=false when the shape is outside its range.
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);

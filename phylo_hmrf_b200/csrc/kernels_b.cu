@@ -487,12 +487,6 @@ int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, do
     return PHMRF_OK;
 }
 
-int estep_grid(int D, int K, int sm_count) {
-    (void)D;
-    (void)K;
-    return sm_count;
-}
-
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s) {
     if (a.n == 0) {
         PHMRF_CUDA(cudaMemsetAsync(a.stats_out, 0, sizeof(double) * (a.K * (1 + a.D + a.D * a.D) + 3), s));

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Attribute ncu warp-stall samples of one kernel to CUDA source lines.
-usage: scripts_ncu_lines.py <rep> <kernel-regex> <cubin> <mangled-substring> [top]
+usage: tools/ncu_lines.py <rep> <kernel-regex> <cubin> <mangled-substring> [top]
 Joins `ncu --page source --csv` (SASS order) with `nvdisasm -g` line info (same order)."""
 import csv
 import re

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Top SASS instructions by stall samples with their dominant stall reasons.
-usage: scripts_ncu_sass.py <rep> <kernel-regex> [top]"""
+usage: tools/ncu_sass.py <rep> <kernel-regex> [top]"""
 import csv, subprocess, sys
 rep, kre = sys.argv[1:3]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40

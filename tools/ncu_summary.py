@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read on the CPU box): per kernel duration, pipes, DRAM bytes, stalls.
-usage: scripts_ncu_summary.py gpurun_out/prof_X.ncu-rep"""
+usage: tools/ncu_summary.py gpurun_out/prof_X.ncu-rep"""
 import csv
 import subprocess
 import sys

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts_prof.sh <tag> <workload> [kernel-regex] [skip] [count]
+# usage: tools/prof.sh <tag> <workload> [kernel-regex] [skip] [count]
 # One ncu launch list + one --set full capture of the named kernels (1 GPU only).
 TAG=$1; WL=$2; KRE=${3:-"emit_kernel|estep_kernel|quantise_unary"}; SKIP=${4:-9}; CNT=${5:-3}
 mkdir -p gpurun_out
