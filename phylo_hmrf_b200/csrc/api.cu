@@ -311,6 +311,7 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
     if (n_own > 0) {
         TRY(ensure_scratch(r, n_own * D));
         if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
+            cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess ||
             cudaMemcpyAsync(r->d_scratch, X, sizeof(double) * n_own * D, cudaMemcpyHostToDevice, r->stream) !=
                 cudaSuccess) {
             cudaError_t err = cudaGetLastError();
@@ -433,7 +434,8 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
     TRY(dev_alloc(r, &r->d_partials, (int64_t)ctx->sm_count * ((int64_t)K * F + 3)));
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
     TRY(dev_alloc(r, &r->d_flags, 1));
-    if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess) {
+    if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
+        cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess) {
         cudaError_t err = cudaGetLastError();
         cudaFree(dXw);
         phmrf_region_destroy(r);

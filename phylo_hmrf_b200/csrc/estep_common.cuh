@@ -39,10 +39,19 @@ __host__ __device__ constexpr int tile_stride(int T, int ntiles) {
 // polynomial (2.2e-13 relative, three orders below the 1e-9 parity tolerance).  CHECK=false assumes 0 <= t < 700 (results are normal numbers); CHECK=true
 // additionally flushes results below 2^-1021 -- and any argument the magic-constant
 // reduction cannot represent, i.e. t <= -2^27 -- to zero; arguments must not exceed +700.
-template <int N, bool CHECK>
+// CHECK=2 instead clamps the argument from below at about -704 with one integer instruction
+// (unsigned minimum on the high word): results that would be below exp(-705) ~ 7e-307 come
+// out as a number in [exp(-705), exp(-704)] rather than 0 -- for soft-max terms whose sum is
+// at least 1 that is an absolute error below 1e-306.
+template <int N, int CHECK>
 __device__ __forceinline__ void exp_batch(double (&t)[N]) {
     const double kMagic = 6755399441055744.0;
     double sft[N], r[N], p[N];
+    if (CHECK == 2) {
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            t[u] = __hiloint2double((int)min((unsigned)__double2hiint(t[u]), 0xC0860000u), __double2loint(t[u]));
+    }
 #pragma unroll
     for (int u = 0; u < N; ++u) sft[u] = fma(t[u], 1.4426950408889634, kMagic);
 #pragma unroll
@@ -77,7 +86,7 @@ __device__ __forceinline__ void exp_batch(double (&t)[N]) {
         const int n = __double2loint(sft[u]);
         int hi = __double2hiint(p[u]) + n * 1048576;
         int lo = __double2loint(p[u]);
-        if (CHECK) {
+        if (CHECK == 1) {
             // the reduction is valid while sft stays within 2^31 of the magic constant
             const bool valid = (unsigned)(__double2hiint(sft[u]) - 0x4337ffff) <= 1u;
             const bool zero = !valid || n < -1021;

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             }
             // g_s = exp(beta*w_s) per slot, in lock step.  The host only selects this kernel when
             // beta * W * max|w| < 100, so no range checks.  (A slot without neighbour gives 1.)
-            exp_batch<kFastSlots, false>(sw);
+            exp_batch<kFastSlots, 0>(sw);
 
             // ---- soft-max shift = max(logp_li, ~max_k logp_k - 598).  The maximum only has to be
             // right to about one unit, so it is taken on the order-preserving integer image of the
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
                 double tb[EB];
 #pragma unroll
                 for (int u = 0; u < EB; ++u) tb[u] = e[q0 + u] - shift;
-                exp_batch<EB, true>(tb);
+                exp_batch<EB, 2>(tb);
 #pragma unroll
                 for (int u = 0; u < EB; ++u) e[q0 + u] = tb[u];
             }
@@ -402,7 +402,7 @@ int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handle
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     *handled = false;
     if (!a.potts || a.W > kFastSlots || a.pp_soa != nullptr || a.n == 0) return PHMRF_OK;
-    if (!(a.s_bound < 100.0)) return PHMRF_OK;  // exp(S) * exp(600) must stay finite without range checks
+    if (!(fabs(a.s_bound) < 100.0)) return PHMRF_OK;  // exp(S) * exp(600) must stay finite without range checks
     switch (a.D) {
 #define PHMRF_CASE(DD) \
     case DD:           \

@@ -73,6 +73,48 @@ __global__ void __launch_bounds__(256) dmma_kernel(double *out, int iters, doubl
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Few-warp issue probe: one CTA per SM, warps 0-3 (one per sub-partition) issue DMMA with NACC
+// independent accumulators, the next `prod` warps issue DFMA in ILP independent chains.
+// Every warp records its own cycle count; out[0] = mean cycles per DFMA instruction of a
+// producer warp, out[1] = mean cycles per DMMA of a consumer warp (block 0).
+template <int ILP, int NACC>
+__global__ void __launch_bounds__(512, 1) mix_kernel(double *out, long long *cyc, int it_dfma, int it_dmma, int cons) {
+    const int warp = threadIdx.x >> 5;
+    const double m = 0.999999, c = 1e-9;
+    double s = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < cons) {
+        double acc[NACC][2];
+#pragma unroll
+        for (int u = 0; u < NACC; ++u) acc[u][0] = acc[u][1] = 0.0;
+        const double a = 1.0 + threadIdx.x * 1e-3, b = 1.0 - 1e-6;
+        for (int it = 0; it < it_dmma; ++it) {
+#pragma unroll
+            for (int u = 0; u < NACC; ++u)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[u][0]), "+d"(acc[u][1]) : "d"(a), "d"(b));
+        }
+#pragma unroll
+        for (int u = 0; u < NACC; ++u) s += acc[u][0] + acc[u][1];
+    } else {
+        double x[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) x[u] = 1.0 + threadIdx.x + u;
+        for (int it = 0; it < it_dfma; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) x[u] = fma(x[u], m, c);
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) s += x[u];
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) cyc[warp] = t1 - t0;
+    if (s == 123.456) out[threadIdx.x] = s;
+}
+
 __global__ void copy_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = in[i];
@@ -150,6 +192,37 @@ int run_probe(int which, double *out) {
         cudaFree(b);
         if (rc != PHMRF_OK) return rc;
         *out = 2.0 * sizeof(double2) * (double)n / (ms * 1e-3) / 1e9;
+        return PHMRF_OK;
+    }
+    if (which >= 7 && which <= 14) {
+        // 7: 8 DFMA warps (ILP 8) alone   8: 4 DFMA warps alone   9: 4 DMMA warps alone (28 acc)
+        // 10/11: 4 DMMA + 8 DFMA(ILP 8): cycles per DFMA / per DMMA
+        // 12/13: 4 DMMA + 8 DFMA(ILP 4): cycles per DFMA / per DMMA     14: 12 DFMA warps alone (ILP 8)
+        long long *cyc = nullptr;
+        PHMRF_CUDA(cudaMalloc(&buf, sizeof(double) * 1024));
+        PHMRF_CUDA(cudaMalloc(&cyc, sizeof(long long) * 16));
+        PHMRF_CUDA(cudaMemset(cyc, 0, sizeof(long long) * 16));
+        const int cons = (which == 7 || which == 8 || which == 14) ? 0 : 4;
+        const int prod = which == 9 ? 0 : (which == 8 ? 4 : (which == 14 ? 12 : 8));
+        const int it_dfma = 4000, it_dmma = 1200;
+        const int threads = 32 * (cons + prod);
+        for (int r = 0; r < 3; ++r) {
+            if (which == 12 || which == 13)
+                mix_kernel<4, 28><<<sms, threads>>>(buf, cyc, it_dfma * 2, it_dmma, cons);
+            else
+                mix_kernel<8, 28><<<sms, threads>>>(buf, cyc, it_dfma, it_dmma, cons);
+        }
+        PHMRF_CUDA(cudaDeviceSynchronize());
+        count_launch(3);
+        long long h[16];
+        PHMRF_CUDA(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(buf);
+        cudaFree(cyc);
+        double cd = 0, cm = 0;
+        for (int w = 0; w < cons; ++w) cm += (double)h[w] / cons;
+        for (int w = cons; w < cons + prod; ++w) cd += (double)h[w] / prod;
+        const bool want_dmma = which == 9 || which == 11 || which == 13;
+        *out = want_dmma ? cm / (it_dmma * 28.0) : cd / (it_dfma * 64.0);
         return PHMRF_OK;
     }
     set_error("unknown probe");
