@@ -292,7 +292,7 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
         return rc;                 \
     }
     TRY(dev_alloc(r, &r->d_X, (int64_t)D * ld));
-    TRY(dev_alloc(r, &r->d_logp, (int64_t)K * ld));
+    TRY(dev_alloc(r, &r->d_logp, (int64_t)logp_rows(K) * ld));
     TRY(dev_alloc(r, &r->d_unary, n_own * K));
     TRY(dev_alloc(r, &r->d_labels, n_window));
     TRY(dev_alloc(r, &r->d_nbr_id, (int64_t)W * ld));
@@ -312,6 +312,7 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
         TRY(ensure_scratch(r, n_own * D));
         if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
             cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess ||
+            launch_fill(r->d_logp + (int64_t)K * ld, kLogpPad, (int64_t)(logp_rows(K) - K) * ld, r->stream) != PHMRF_OK ||
             cudaMemcpyAsync(r->d_scratch, X, sizeof(double) * n_own * D, cudaMemcpyHostToDevice, r->stream) !=
                 cudaSuccess) {
             cudaError_t err = cudaGetLastError();
@@ -420,7 +421,7 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
                           nullptr, nullptr, nullptr, nullptr, &n_edges, nullptr, r->stream));
     r->E = n_edges;
     TRY(dev_alloc(r, &r->d_X, (int64_t)D * ld));
-    TRY(dev_alloc(r, &r->d_logp, (int64_t)K * ld));
+    TRY(dev_alloc(r, &r->d_logp, (int64_t)logp_rows(K) * ld));
     TRY(dev_alloc(r, &r->d_unary, n_own * K));
     TRY(dev_alloc(r, &r->d_labels, n_window));
     TRY(dev_alloc(r, &r->d_nbr_id, (int64_t)r->W * ld));
@@ -435,7 +436,8 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
     TRY(dev_alloc(r, &r->d_flags, 1));
     if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
-        cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess) {
+        cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess ||
+        launch_fill(r->d_logp + (int64_t)K * ld, kLogpPad, (int64_t)(logp_rows(K) - K) * ld, r->stream) != PHMRF_OK) {
         cudaError_t err = cudaGetLastError();
         cudaFree(dXw);
         phmrf_region_destroy(r);

@@ -41,6 +41,11 @@ int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t 
 // pattern of a non-negative double, atomicMax).
 int launch_emit(const double *X_soa, int64_t n, int64_t ld, int D, int K, const double *model_global,
                 double *logp, unsigned long long *absmax_bits, int sm_count, cudaStream_t s);
+int launch_fill(double *p, double v, int64_t count, cudaStream_t s);
+// rows of the log-likelihood matrix: K rounded up to the 8-state tiles of the pipeline kernel;
+// the padding rows hold kLogpPad for the lifetime of a region
+inline int logp_rows(int K) { return (K + 7) / 8 * 8; }
+constexpr double kLogpPad = -1.0e6;
 // dwf = max(absmax_u, wmax*vmax) + 1e-10 unless dwf_in > 0; written to *dwf_dev.
 int launch_dwf(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in, double *dwf_dev,
                cudaStream_t s);

@@ -226,6 +226,11 @@ int launch_emit(const double *Xs, int64_t n, int64_t ld, int D, int K, const dou
 // ------------------------------------------------------------------------------------
 // dwf = max(max|unary|, max|w| * max V) + 1e-10   (pygco, down_weight_factor=None)
 // ------------------------------------------------------------------------------------
+__global__ void fill_kernel(double *p, double v, int64_t count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
 __global__ void dwf_kernel(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in,
                            double *dwf_dev) {
     if (dwf_in > 0.0) {
@@ -238,6 +243,15 @@ __global__ void dwf_kernel(const unsigned long long *absmax_bits, double wmax, d
         dwf_dev[0] = __dadd_rn(m, 1e-10);
     }
     dwf_dev[1] = __longlong_as_double((long long)absmax_bits[0]);
+}
+
+int launch_fill(double *p, double v, int64_t count, cudaStream_t s) {
+    if (count <= 0) return PHMRF_OK;
+    const int64_t blocks = (count + 255) / 256;
+    fill_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(p, v, count);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
 }
 
 int launch_dwf(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in, double *dwf_dev,

@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             {
                 const double *pk = a.logp + i;
 #pragma unroll
-                for (int q = 0; q < KP; ++q) {
-                    e[q] = q < K ? *pk : -1.0e6;
+                for (int q = 0; q < KP; ++q) {  // rows K..KP-1 hold kLogpPad (phmrf_region_create)
+                    e[q] = *pk;
                     pk += ld;
                 }
             }
@@ -233,14 +233,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
 #pragma unroll
             for (int c = 0; c < KP; c += 2) {
                 double2 v = *reinterpret_cast<const double2 *>(Prow + c);
-                if (c < K) qsum += v.x;
-                if (c + 1 < K) qsum += v.y;
+                qsum += v.x + v.y;
                 v.x *= e[c];
                 v.y *= e[c + 1];
                 esum += v.x + v.y;
                 *reinterpret_cast<double2 *>(Prow + c) = v;
             }
-            // soft-max of -pp at the node's own label: exp(S_li) / sum_k exp(S_k)
+            // soft-max of -pp at the node's own label: exp(S_li) / sum_k exp(S_k); the padding
+            // states have no neighbour, G = 1 exactly
+            qsum -= (double)(KP - K);
             const double pwn_log = log(g_li / qsum + 1e-16);
             const bool bad = !(esum <= DBL_MAX) || !(qsum <= DBL_MAX) || !(esum > 0.0);
             bad_any |= bad ? 1 : 0;
