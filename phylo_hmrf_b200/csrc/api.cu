@@ -53,6 +53,9 @@ struct phmrf_region {
     int32_t *d_labels = nullptr; // [n_window]
     int32_t *d_nbr_id = nullptr; // [W][ld]
     double *d_nbr_w = nullptr;   // [W][ld]
+    double *d_nbr_g = nullptr;   // [W][ld] exp(beta*w), built on first use for (g_beta, g_weighted)
+    double g_beta = 0.0;
+    int g_weighted = -1;
     double *d_edge_w = nullptr;  // [E]
     int32_t *d_edge_wi = nullptr;
     long long *d_edge_ids = nullptr;  // [E,2] window-local, only for regions built by phmrf_region_create_grid
@@ -506,6 +509,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     cudaFree(r->d_labels);
     cudaFree(r->d_nbr_id);
     cudaFree(r->d_nbr_w);
+    cudaFree(r->d_nbr_g);
     cudaFree(r->d_edge_w);
     cudaFree(r->d_edge_wi);
     cudaFree(r->d_edge_ids);
@@ -713,6 +717,24 @@ static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, boo
     a.flags = r->d_flags;
     a.force_general = force_general ? 1 : 0;
     a.s_bound = ctx->beta * r->W * (estimate_type == 3 ? r->wmax : 1.0);
+    a.nbr_g = nullptr;
+    a.exp_beta = std::exp(ctx->beta);
+    if (ctx->potts && !force_general && !want_pp && r->W > 0 && std::fabs(a.s_bound) < 100.0) {
+        // per-slot factors of the pipeline kernel: constant while beta and the weights are
+        const int weighted = estimate_type == 3 ? 1 : 0;
+        if (!r->d_nbr_g) {
+            if ((rc = dev_alloc(r, &r->d_nbr_g, (int64_t)r->W * r->ld)) != PHMRF_OK) return rc;
+            r->g_weighted = -1;
+        }
+        if (r->g_weighted != weighted || r->g_beta != ctx->beta) {
+            if ((rc = launch_nbr_g(r->d_nbr_id, r->d_nbr_w, r->d_nbr_g, (int64_t)r->W * r->ld, ctx->beta, weighted,
+                                   r->stream)) != PHMRF_OK)
+                return rc;
+            r->g_weighted = weighted;
+            r->g_beta = ctx->beta;
+        }
+        a.nbr_g = r->d_nbr_g;
+    }
     PHMRF_CUDA(cudaMemsetAsync(r->d_flags, 0, sizeof(int), r->stream));
     return launch_estep(a, ctx->sm_count, r->stream);
 }

@@ -76,7 +76,12 @@ struct EstepArgs {
     int *flags;               // [1] device flag: bit 0 = the pipeline met an overflow, rerun on the general path
     int force_general;        // skip the pipeline kernel
     double s_bound;           // upper bound of any neighbour weight sum: beta * W * max|w|
+    const double *nbr_g;      // [W][ld] exp(beta * w) per slot (1 for an empty slot); pipeline kernel only
+    double exp_beta;          // exp(beta)
 };
+// g[s][i] = exp(beta * (weighted ? w[s][i] : 1)) for occupied slots, 1 otherwise (kernels_b2.cu)
+int launch_nbr_g(const int32_t *nbr_id, const double *nbr_w, double *nbr_g, int64_t count, double beta, int weighted,
+                 cudaStream_t s);
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s);
 // Warp-specialised pipeline (kernels_b2.cu); *handled=false when the shape is outside its range.
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);

@@ -141,12 +141,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
                     for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (q >> 1) * ld + i2 + (q & 1) * 16);
                     if (lane < 2 * D) prefetch_l2(a.X_soa + (lane >> 1) * ld + i2 + (lane & 1) * 16);
                     if (lane < 2 * W) prefetch_l2(a.nbr_w + (lane >> 1) * ld + i2 + (lane & 1) * 16);
+                    if (lane >= 16 && lane - 16 < 2 * W)
+                        prefetch_l2(a.nbr_g + ((lane - 16) >> 1) * ld + i2 + (lane & 1) * 16);
                     if (lane < W) prefetch_l2(a.nbr_id + lane * ld + i2);
                 }
             }
             // ---- loads first: neighbour ids and own label, then what depends on them.
             int lab[kFastSlots];
-            double sw[kFastSlots];
+            double sw[kFastSlots], gw[kFastSlots];  // beta*w_s and g_s = exp(beta*w_s) (precomputed, 1 if empty)
             int li;
             double lp_li;
             {
@@ -159,10 +161,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
                 }
                 li = a.labels[a.own_offset + i];
                 const double *pw = a.nbr_w + i;
+                const double *pg = a.nbr_g + i;
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) {
                     sw[s] = (s < W && weighted) ? *pw : 1.0;
+                    gw[s] = s < W ? *pg : 1.0;
                     pw += ld;
+                    pg += ld;
                 }
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1;
@@ -189,11 +194,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             }
             if (all_neg < 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
                 lab[0] = li;
-                sw[0] = beta;
+                gw[0] = a.exp_beta;
             }
-            // g_s = exp(beta*w_s) per slot, in lock step.  The host only selects this kernel when
-            // beta * W * max|w| < 100, so no range checks.  (A slot without neighbour gives 1.)
-            exp_batch<kFastSlots, 0>(sw);
+            // (the host only selects this kernel when |beta| * W * max|w| < 100: the products of
+            // the g_s below stay finite)
 
             // ---- soft-max shift = max(logp_li, ~max_k logp_k - 598).  The maximum only has to be
             // right to about one unit, so it is taken on the order-preserving integer image of the
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             for (int c = 0; c < KP; c += 2) *reinterpret_cast<double2 *>(Prow + c) = make_double2(1.0, 1.0);
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                if (lab[s] >= 0) Prow[lab[s]] *= sw[s];
+                if (lab[s] >= 0) Prow[lab[s]] *= gw[s];
             }
             const double g_li = Prow[li];
             // e_k = exp(logp_k - shift) * G_k, written over G; Q = sum_k G_k on the way
@@ -398,11 +402,27 @@ int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handle
     }
 }
 
+__global__ void nbr_g_kernel(const int32_t *__restrict__ nbr_id, const double *__restrict__ nbr_w,
+                             double *__restrict__ nbr_g, int64_t count, double beta, int weighted) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        nbr_g[i] = nbr_id[i] >= 0 ? exp(beta * (weighted ? nbr_w[i] : 1.0)) : 1.0;
+}
+
 }  // namespace
+
+int launch_nbr_g(const int32_t *nbr_id, const double *nbr_w, double *nbr_g, int64_t count, double beta, int weighted,
+                 cudaStream_t s) {
+    if (count <= 0) return PHMRF_OK;
+    const int64_t blocks = (count + 255) / 256;
+    nbr_g_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, s>>>(nbr_id, nbr_w, nbr_g, count, beta, weighted);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
 
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     *handled = false;
-    if (!a.potts || a.W > kFastSlots || a.pp_soa != nullptr || a.n == 0) return PHMRF_OK;
+    if (!a.potts || a.W > kFastSlots || a.pp_soa != nullptr || a.n == 0 || a.nbr_g == nullptr) return PHMRF_OK;
     if (!(fabs(a.s_bound) < 100.0)) return PHMRF_OK;  // exp(S) * exp(600) must stay finite without range checks
     switch (a.D) {
 #define PHMRF_CASE(DD) \
