@@ -99,3 +99,29 @@ def test_every_feature_count_and_state_tiling(ph, d, K):
     X, e, w, means, covars = _data(10 + d, 26, d, K)
     lab = np.random.default_rng(d).integers(0, K, size=len(X))
     _check(ph, X, e, w, means, covars, synth.potts(K, 1.0), lab, 3)
+
+
+def test_slot_factor_cache_follows_beta_and_weighting(ph):
+    """The pipeline keeps exp(beta*w) per neighbour slot on the device between E-steps of one
+    region: a new beta (set_model) or a switch between weighted and unweighted estimates must
+    rebuild it."""
+    from phylo_hmrf_b200 import synth
+    X, e, w, means, covars = _data(11, 30, 5, 12)
+    K, d = means.shape
+    lab = np.random.default_rng(11).integers(0, K, size=len(X))
+    lp_ref = orc.compute_log_likelihood(X, means, covars)
+    m = ph.Model(K, d)
+    m.set_model(means, covars, synth.potts(K, 0.7))
+    reg = m.region(X, e, w)
+    reg.emit_loglik()
+    reg.set_labels(lab)
+    for beta, et in ((0.7, 3), (0.7, 0), (1.9, 0), (1.9, 3), (0.7, 3)):
+        V = synth.potts(K, beta)
+        m.set_model(means, covars, V)
+        reg.emit_loglik()
+        stats, sums, post = reg.estep_stats(et, want_post=True)
+        ref = orc.compute_posteriors_graph(V, lab, lp_ref, w, e, None, et, faithful=False, stable=True)
+        np.testing.assert_allclose(post, ref[0], rtol=RTOL, atol=1e-290, err_msg=f"beta={beta} et={et}")
+        np.testing.assert_allclose(ph.costs_from_sums(sums, len(X)), ref[1:], rtol=RTOL, atol=1e-12)
+    reg.close()
+    m.close()
