@@ -35,8 +35,8 @@ __host__ __device__ constexpr int tile_stride(int T, int ntiles) {
 }
 
 // N independent exponentials evaluated in lock step (explicit instruction-level
-// parallelism for warps that cannot rely on occupancy): same reduction as exp_sm, degree-10
-// polynomial (2.2e-13 relative, three orders below the 1e-9 parity tolerance).  CHECK=false assumes 0 <= t < 700 (results are normal numbers); CHECK=true
+// parallelism for warps that cannot rely on occupancy): same reduction as exp_sm, degree-9
+// polynomial (7e-12 relative, two orders below the 1e-9 parity tolerance).  CHECK=false assumes 0 <= t < 700 (results are normal numbers); CHECK=true
 // additionally flushes results below 2^-1021 -- and any argument the magic-constant
 // reduction cannot represent, i.e. t <= -2^27 -- to zero; arguments must not exceed +700.
 // CHECK=2 instead clamps the argument from below at about -704 with one integer instruction
@@ -60,11 +60,9 @@ __device__ __forceinline__ void exp_batch(double (&t)[N]) {
         r[u] = fma(fn, -6.93147180559945286e-01, t[u]);
         r[u] = fma(fn, -2.31904681384629956e-17, r[u]);
     }
-    // degree-10 Taylor polynomial on |r| <= ln2/2: truncation error < 2.2e-13 relative
+    // degree-9 Taylor polynomial on |r| <= ln2/2: truncation error < 7e-12 relative
 #pragma unroll
-    for (int u = 0; u < N; ++u) p[u] = fma(2.75573192239858907e-07, r[u], 2.75573192239858907e-06);
-#pragma unroll
-    for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 2.48015873015873016e-05);
+    for (int u = 0; u < N; ++u) p[u] = fma(2.75573192239858907e-06, r[u], 2.48015873015873016e-05);
 #pragma unroll
     for (int u = 0; u < N; ++u) p[u] = fma(p[u], r[u], 1.98412698412698413e-04);
 #pragma unroll
@@ -150,6 +148,17 @@ __device__ __forceinline__ void write_y_row(double *Yrow, const double (&x)[D], 
     ((*reinterpret_cast<double2 *>(Yrow + 2 * Cs) =
           make_double2(y_at<D, TF, TFs, 2 * Cs>(x, xs, inv), y_at<D, TF, TFs, 2 * Cs + 1>(x, xs, inv))),
      ...);
+}
+
+// 1/a for a normal, positive a: hardware seed + two Newton steps (full double precision up to
+// an ulp or two; no IEEE rounding or special-case branches like the `/` operator).
+__device__ __forceinline__ double fast_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    return fma(x, e, x);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -246,10 +246,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             // soft-max of -pp at the node's own label: exp(S_li) / sum_k exp(S_k); the padding
             // states have no neighbour, G = 1 exactly
             qsum -= (double)(KP - K);
-            const double pwn_log = log(g_li / qsum + 1e-16);
+            const double pwn_log = log(fma(g_li, fast_rcp(qsum), 1e-16));
             const bool bad = !(esum <= DBL_MAX) || !(qsum <= DBL_MAX) || !(esum > 0.0);
             bad_any |= bad ? 1 : 0;
-            const double inv = valid ? 1.0 / esum : 0.0;
+            const double inv = valid ? fast_rcp(esum) : 0.0;
             {
                 double x[D], xs[D];
                 const double *px = a.X_soa + i;
