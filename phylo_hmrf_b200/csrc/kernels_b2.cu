@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             }
             // ---- loads first: neighbour ids and own label, then what depends on them.
             int lab[kFastSlots];
-            double sw[kFastSlots], gw[kFastSlots];  // beta*w_s and g_s = exp(beta*w_s) (precomputed, 1 if empty)
+            double sw[kFastSlots], gw[kFastSlots];  // w_s and g_s = exp(beta*w_s) (precomputed, 1 if empty)
             int li;
             double lp_li;
             {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
                 const double *pg = a.nbr_g + i;
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) {
-                    sw[s] = (s < W && weighted) ? *pw : 1.0;
+                    sw[s] = (s < W && weighted) ? *pw : 0.0;
                     gw[s] = s < W ? *pg : 1.0;
                     pw += ld;
                     pg += ld;
@@ -188,10 +188,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
             double pc = 0.0;   // sum over the incident edges of V[l_nbr, l_i] * w
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
-                sw[s] = lab[s] >= 0 ? beta * sw[s] : 0.0;
+                // an empty slot has label -1 and stored weight 0; unweighted estimates count 1 per edge
+                const double ws = weighted ? sw[s] : (lab[s] >= 0 ? 1.0 : 0.0);
                 all_neg &= lab[s];
-                pc += lab[s] != li ? sw[s] : 0.0;  // an empty slot has weight 0
+                pc += lab[s] != li ? ws : 0.0;
             }
+            pc *= beta;
             if (all_neg < 0) {  // isolated node: pp = V[label] unweighted (phylo_hmrf.py:421-423)
                 lab[0] = li;
                 gw[0] = a.exp_beta;
