@@ -283,7 +283,7 @@ __device__ __forceinline__ double div_by_dwf(double u, double dwf, double y) {
 // coalesced), converts, stages the 32 x K integers in its own shared-memory tile and streams
 // them out as one contiguous 128*K-byte run.  No block-wide barrier: the warps of a CTA are
 // independent, so loads of one overlap stores of another.
-__global__ void __launch_bounds__(256) quantise_unary_kernel(const double *__restrict__ logp, int64_t n, int64_t ld,
+__global__ void __launch_bounds__(256, 4) quantise_unary_kernel(const double *__restrict__ logp, int64_t n, int64_t ld,
                                                               int K, const double *__restrict__ dwf_dev, double tol,
                                                               int32_t *__restrict__ unary,
                                                               long long *__restrict__ blist, long long bcap,
@@ -356,7 +356,7 @@ int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, cons
         PHMRF_CUDA(cudaFuncSetAttribute(quantise_unary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (n + 31) / 32;
     const int64_t blocks = (n_tiles + warps - 1) / warps;
-    const int64_t cap = (int64_t)sm_count * 6;
+    const int64_t cap = (int64_t)sm_count * 4;  // one resident wave (4 CTAs/SM at <= 64 registers)
     const int grid = (int)(blocks < cap ? blocks : cap);
     quantise_unary_kernel<<<grid, warps * 32, smem, s>>>(logp, n, ld, K, dwf_dev, tol, unary, blist, bcap, bcount);
     count_launch();
