@@ -1,0 +1,56 @@
+"""The preprocessing oracle (oracle/prep_oracle.py) against fixtures produced by the reference's own
+functions (tests/golden/make_golden_prep.py): bit-identical, both are NumPy float64 in the same
+operation order."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import prep_oracle as po
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "prep_cases.npz"))
+NAMES = [str(n) for n in G["names"]]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_normalize_feature(name):
+    p = "prep_%s_" % name
+    for tag, xmin, xmax in (("auto", -1, -1), ("fixed", 0.0, 40.0)):
+        x1, vec1, lo, hi = po.normalize_feature(G[p + "value"], xmin, xmax)
+        np.testing.assert_array_equal(x1, G[p + "norm_" + tag])
+        np.testing.assert_array_equal(vec1, G[p + "vec1_" + tag])
+        np.testing.assert_array_equal([lo, hi], G[p + "lim_" + tag])
+    np.testing.assert_array_equal(po.log_transform(G[p + "norm_auto"]), G[p + "x"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_image_holefill_flatten(name):
+    p = "prep_%s_" % name
+    mtx, start = po.matrix_image(G[p + "x"], G[p + "pos"])
+    np.testing.assert_array_equal(mtx, G[p + "mtx"])
+    assert start == int(G[p + "start"][0])
+    filled = np.stack([po.near_interpolation1(mtx[:, :, c].copy()) for c in range(mtx.shape[2])], axis=2)
+    np.testing.assert_array_equal(filled, G[p + "filled"])
+    assert (filled != mtx).any(), "fixture must exercise the hole fill"
+    np.testing.assert_array_equal(po.near_interpolation1a(G[p + "rect"].copy()), G[p + "rect_filled"])
+    data1, pos_idx, serial = po.matrix_array(filled, start, 1)
+    np.testing.assert_array_equal(data1, G[p + "data1"])
+    np.testing.assert_array_equal(pos_idx, G[p + "pos_idx"])
+    np.testing.assert_array_equal(serial, G[p + "serial"])
+
+
+def test_diffusion_restatement_properties():
+    """medpy is absent (parity unpinned): check what the published scheme guarantees -- a constant
+    image is a fixed point, the total is conserved (zero-flux borders), symmetric in -> symmetric
+    out, and the result is float32."""
+    rng = np.random.default_rng(0)
+    a = rng.random((17, 17)) * 5
+    a = a + a.T
+    out = po.anisotropic_diffusion(a, niter=5, kappa=50, gamma=0.1)
+    assert out.dtype == np.float32
+    np.testing.assert_array_equal(out, out.T)
+    assert abs(out.astype(np.float64).sum() - a.astype(np.float32).astype(np.float64).sum()) < 1e-2
+    c = np.full((9, 11), 3.25)
+    np.testing.assert_array_equal(po.anisotropic_diffusion(c, niter=3), c.astype(np.float32))
+    # smoothing: the variance does not grow
+    assert out.var() <= a.var()
