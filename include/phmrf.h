@@ -181,6 +181,36 @@ int64_t phmrf_region_n_window(const phmrf_region *r);
 int64_t phmrf_region_own_offset(const phmrf_region *r);
 int phmrf_region_edges(phmrf_region *r, int64_t *edge_ids_out, double *edge_w_out);
 
+/* ------------------------------------------------------------------ preprocessing ----- */
+
+/* Per-species rescale to a common range followed by the log transform (utility.py:867-897
+ * normalize_feature, utility.py:362 x = log(1 + x1)).  x is [n,d] row-major on the host and is
+ * transformed in place: negatives are clamped to 0, column i is mapped linearly from its own
+ * [min_i, max_i] to [x_min, x_max]; a negative *x_min / *x_max selects the median of the column
+ * minima / maxima and the value used is written back.  colminmax_out is [d,2].  log1p != 0
+ * applies log(1 + x) afterwards. */
+int phmrf_prep_normalise(int device, double *x, int64_t n, int d, double *x_min, double *x_max, double *colminmax_out,
+                         int log1p);
+
+/* One region's contact image and its node features (utility.py:1519-1598
+ * write_matrix_image_Ctrl_unsym1 for kind 1, :1704-1783 write_matrix_image_Ctrl_sym1 for kind 0,
+ * without the edge list -- phmrf_grid_edges / phmrf_region_create_grid build that):
+ *   1. scatter the n bin pairs value[i,:] at (pos[i,0]-start1, pos[i,1]-start2) into an n1 x n2 x d
+ *      image (kind 1: n1 == n2, start1 == start2, written symmetrically; utility.py:2192-2226,
+ *      2332-2365).  A pair listed twice keeps one of its values, unspecified which (the
+ *      reference keeps the last);
+ *   2. per species, the 3x3 median hole fill in the reference's sequential raster order
+ *      (utility.py:603-659; executed as a 2i+j wavefront, which preserves every dependency);
+ *   3. filter_mode 0: Perona-Malik anisotropic diffusion, niter steps, conduction
+ *      exp(-(delta/kappa)^2), step gamma, float32 like medpy's implementation (the call at
+ *      utility.py:1566-1573); any other filter_mode: no filter;
+ *   4. nodes in the reference's order: the upper triangle row by row (kind 1) or the whole block
+ *      (kind 0) -> data_out [n_nodes, d] row-major (utility.py:2295-2329, 2368-2400).
+ * image_out (nullable) receives the filtered image [n1, n2, d]. */
+int phmrf_prep_region_image(int device, const double *value, const int64_t *pos, int64_t n, int d, int kind,
+                            int64_t start1, int64_t start2, int64_t n1, int64_t n2, int filter_mode, int niter,
+                            double kappa, double gamma, double *data_out, double *image_out);
+
 /* ------------------------------------------------------------------ probes ------------ */
 
 /* FP64 FMA-pipe peak of the current device, measured with a dependent-chain DFMA

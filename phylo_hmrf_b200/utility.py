@@ -58,3 +58,83 @@ def _maybe_write(edge_list, output_filename):
         data2 = pd.DataFrame({'id1': np.int64(edge_list[:, 0]), 'id2': np.int64(edge_list[:, 1]),
                               'weight': edge_list[:, 2]})
         data2.to_csv(output_filename, index=False, header=False, sep='\t')
+
+
+# ---- per-region preprocessing (image pipeline) ---------------------------------
+
+def normalize_feature(x1, x_min, x_max, device=0):
+    """utility.py:867-897.  Returns (x1, vec1, x_min, x_max); like the reference, ``x1`` is
+    transformed in place when it is a C-contiguous float64 array."""
+    return _normalise(x1, x_min, x_max, 0, device)
+
+
+def normalize_log_feature(x1, x_min, x_max, device=0):
+    """normalize_feature followed by ``x = np.log(1 + x1)`` (utility.py:358-362) in one pass."""
+    return _normalise(x1, x_min, x_max, 1, device)
+
+
+def _normalise(x1, x_min, x_max, log1p, device):
+    x = x1 if (isinstance(x1, np.ndarray) and x1.dtype == np.float64 and x1.flags.c_contiguous) else as_f64(x1)
+    if x.ndim != 2 or x.size == 0:
+        raise ValueError("x1 must be a non-empty [n_samples, n_species] array")
+    lo, hi = C.c_double(float(x_min)), C.c_double(float(x_max))
+    vec1 = np.empty((x.shape[1], 2), dtype=np.float64)
+    check(_lib.lib().phmrf_prep_normalise(int(device), dptr(x), x.shape[0], x.shape[1], C.byref(lo), C.byref(hi),
+                                          dptr(vec1), int(log1p)))
+    return x, vec1, lo.value, hi.value
+
+
+def _region_image(value, pos, kind, filter_mode, filter_param1, filter_param2, want_image, device):
+    value = as_f64(value)
+    pos = np.ascontiguousarray(np.asarray(pos), dtype=np.int64)
+    if value.ndim != 2 or pos.shape != (value.shape[0], 2) or value.shape[0] == 0:
+        raise ValueError("value must be [n, d] and pos [n, 2]")
+    d = value.shape[1]
+    s1, s2 = int(pos[:, 0].min()), int(pos[:, 1].min())
+    e1, e2 = int(pos[:, 0].max()), int(pos[:, 1].max())
+    if kind == 1:  # utility.py:2204-2211: one square window over both coordinates
+        s1 = s2 = min(s1, s2)
+        n1 = n2 = max(e1, e2) - s1 + 1
+        n_nodes = n1 * (n1 + 1) // 2
+    else:          # utility.py:2341-2346
+        n1, n2 = e1 - s1 + 1, e2 - s2 + 1
+        n_nodes = n1 * n2
+    if filter_mode == 0:
+        niter, kappa = (10, 50.0) if filter_param1 < 0 else (int(filter_param1), float(filter_param2))
+    elif filter_mode in (1, 2):
+        raise NotImplementedError("filter_mode 1 (bilateral) and 2 (Gaussian) are not built; the reference's "
+                                  "pipeline uses filter_mode 0 (utility.py:411-412)")
+    else:
+        niter, kappa = 0, 50.0
+    data1 = np.empty((n_nodes, d), dtype=np.float64)
+    mtx1 = np.empty((n1, n2, d), dtype=np.float64) if want_image else None
+    check(_lib.lib().phmrf_prep_region_image(int(device), dptr(value), pos.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             value.shape[0], d, kind, s1, s2, n1, n2, 0 if filter_mode == 0 else -1,
+                                             niter, kappa, 0.1, dptr(data1),
+                                             dptr(mtx1) if want_image else None))
+    return data1, mtx1, (s1, s2), (n1, n2)
+
+
+def write_matrix_image_Ctrl_unsym1(value, pos, output_filename1, output_filename2, num_neighbor, sigma, type_id,
+                                   filter_mode, filter_param1, filter_param2, device=0, want_image=True):
+    """utility.py:1519-1598 (diagonal region): image, hole fill, anisotropic diffusion, upper-triangle
+    node list and its edge list.  Returns (data1, mtx1, pos_idx, edge_list)."""
+    data1, mtx1, (s1, _), (n1, _) = _region_image(value, pos, 1, filter_mode, filter_param1, filter_param2,
+                                                  want_image, device)
+    ii, jj = np.triu_indices(n1)
+    pos_idx = np.stack([ii, jj], axis=1) + s1
+    edge_list = _edges(data1, 1, n1, n1, num_neighbor, device)
+    _maybe_write(edge_list, output_filename2)
+    return data1, mtx1, pos_idx, edge_list
+
+
+def write_matrix_image_Ctrl_sym1(value, pos, output_filename1, output_filename2, num_neighbor, sigma, type_id,
+                                 filter_mode, filter_param1, filter_param2, device=0, want_image=True):
+    """utility.py:1704-1783 (off-diagonal block).  Returns (data1, mtx1, pos_idx, edge_list)."""
+    data1, mtx1, (s1, s2), (n1, n2) = _region_image(value, pos, 0, filter_mode, filter_param1, filter_param2,
+                                                    want_image, device)
+    ii, jj = np.meshgrid(np.arange(n1), np.arange(n2), indexing="ij")
+    pos_idx = np.stack([ii.ravel() + s1, jj.ravel() + s2], axis=1)
+    edge_list = _edges(data1, 0, n1, n2, num_neighbor, device)
+    _maybe_write(edge_list, output_filename2)
+    return data1, mtx1, pos_idx, edge_list

@@ -1,0 +1,117 @@
+"""Preprocessing stage on the GPU against the oracle and the reference fixtures.
+
+Bit-exact: rescale (no log), image scatter, 3x3 median hole fill (the wavefront order must reproduce
+the reference's sequential raster scan), node order.  Tolerance: the log transform (CUDA log vs
+glibc log, <= 2 ulp: rtol 1e-14) and the diffusion (float32 arithmetic like medpy, CUDA expf vs
+NumPy's float32 exp: rtol 2e-5, atol 2e-6 on the float32 image)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import prep_oracle as po
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "prep_cases.npz"))
+NAMES = [str(n) for n in G["names"]]
+
+
+@pytest.fixture(scope="module")
+def util():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from phylo_hmrf_b200 import utility
+    return utility
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_normalise_against_reference_fixture(util, name):
+    p = "prep_%s_" % name
+    for tag, xmin, xmax in (("auto", -1, -1), ("fixed", 0.0, 40.0)):
+        x1, vec1, lo, hi = util.normalize_feature(G[p + "value"].copy(), xmin, xmax)
+        np.testing.assert_array_equal(x1, G[p + "norm_" + tag])
+        np.testing.assert_array_equal(vec1, G[p + "vec1_" + tag])
+        np.testing.assert_array_equal([lo, hi], G[p + "lim_" + tag])
+    x, _, _, _ = util.normalize_log_feature(G[p + "value"].copy(), -1, -1)
+    np.testing.assert_allclose(x, G[p + "x"], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_image_holefill_nodes_against_reference_fixture(util, name):
+    p = "prep_%s_" % name
+    data1, mtx1, pos_idx, edges = util.write_matrix_image_Ctrl_unsym1(G[p + "x"], G[p + "pos"], "", "", 8, 0, 1,
+                                                                       -1, -1, -1)  # no filter
+    np.testing.assert_array_equal(mtx1, G[p + "filled"])
+    np.testing.assert_array_equal(data1, G[p + "data1"])
+    np.testing.assert_array_equal(pos_idx, G[p + "pos_idx"])
+    assert edges.shape[1] == 3
+
+
+def _random_region(seed, W, d, fill):
+    rng = np.random.default_rng(seed)
+    ii, jj = np.triu_indices(W)
+    keep = rng.random(len(ii)) < fill
+    ii, jj = ii[keep], jj[keep]
+    val = np.log1p((40.0 / (1.0 + (jj - ii)))[:, None] * rng.gamma(2.0, 0.5, size=(len(ii), d)))
+    val[rng.random(val.shape) < 0.05] = 0.0
+    return val, np.stack([ii + 11, jj + 11], axis=1).astype(np.int64)
+
+
+@pytest.mark.parametrize("W,d,fill", [(5, 1, 0.9), (64, 3, 0.6), (257, 2, 0.35)])
+def test_full_pipeline_diag(util, W, d, fill):
+    val, pos = _random_region(W, W, d, fill)
+    ref_nofilter = po.image_pipeline_diag(val, pos, filter_mode=-1)
+    got = util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0, 1, -1, -1, -1)
+    np.testing.assert_array_equal(got[1], ref_nofilter[1])   # hole-filled image, bit for bit
+    np.testing.assert_array_equal(got[0], ref_nofilter[0])
+    ref = po.image_pipeline_diag(val, pos, filter_mode=0, niter=5, kappa=50, gamma=0.1)
+    got = util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0, 1, 0, 5, 50)
+    np.testing.assert_allclose(got[1], ref[1], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(got[0], ref[0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_array_equal(got[2], ref[2])
+    np.testing.assert_array_equal(got[1], np.transpose(got[1], (1, 0, 2)))  # stays symmetric
+    # default filter parameters (filter_param1 < 0): niter=10, kappa=50
+    ref10 = po.image_pipeline_diag(val, pos, filter_mode=0, niter=10, kappa=50, gamma=0.1)
+    got10 = util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0, 1, 0, -1, -1, want_image=False)
+    assert got10[1] is None
+    np.testing.assert_allclose(got10[0], ref10[0], rtol=4e-5, atol=4e-6)
+
+
+def test_off_diagonal_block(util):
+    rng = np.random.default_rng(5)
+    n1, n2, d = 37, 52, 2
+    ii, jj = np.meshgrid(np.arange(n1), np.arange(n2), indexing="ij")
+    keep = rng.random(ii.size) < 0.55
+    ii, jj = ii.ravel()[keep], jj.ravel()[keep]
+    # the extremes must be present so that the window is n1 x n2
+    ii = np.concatenate([ii, [0, n1 - 1]])
+    jj = np.concatenate([jj, [0, n2 - 1]])
+    val = rng.gamma(2.0, 0.7, size=(len(ii), d))
+    pos = np.stack([ii + 100, jj + 300], axis=1).astype(np.int64)
+    mtx = np.zeros((n1, n2, d))
+    for k in range(len(ii)):           # utility.py:2351-2354 (later rows overwrite)
+        mtx[ii[k], jj[k]] = val[k]
+    # drop duplicates for the device scatter (which of two values survives is unspecified there)
+    _, first = np.unique(ii * n2 + jj, return_index=True)
+    last = {}
+    for k in range(len(ii)):
+        last[(ii[k], jj[k])] = k
+    sel = np.array(sorted(last.values()))
+    ref = np.stack([po.near_interpolation1a(mtx[:, :, c].copy()) for c in range(d)], axis=2)
+    got = util.write_matrix_image_Ctrl_sym1(val[sel], pos[sel], "", "", 8, 0, 0, -1, -1, -1)
+    np.testing.assert_array_equal(got[1], ref)
+    np.testing.assert_array_equal(got[0], ref.reshape(n1 * n2, d))
+    assert got[2][0].tolist() == [100, 300] and got[2][-1].tolist() == [100 + n1 - 1, 300 + n2 - 1]
+    refd = np.stack([po.anisotropic_diffusion(ref[:, :, c], 5, 50, 0.1) for c in range(d)], axis=2)
+    gotd = util.write_matrix_image_Ctrl_sym1(val[sel], pos[sel], "", "", 8, 0, 0, 0, 5, 50)
+    np.testing.assert_allclose(gotd[1], refd, rtol=2e-5, atol=2e-6)
+
+
+def test_rejects_pairs_outside_the_window_and_unbuilt_filters(util):
+    val = np.ones((3, 1))
+    pos = np.array([[0, 0], [1, 2], [2, 2]], dtype=np.int64)
+    with pytest.raises(NotImplementedError):
+        util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0, 1, 1, -1, -1)
+    with pytest.raises(ValueError):
+        util.normalize_feature(np.zeros((0, 3)), -1, -1)
