@@ -270,9 +270,12 @@ extern "C" int phmrf_prep_region_image(int device, const double *value, const in
     const int64_t npix = n1 * n2;
     const int64_t n_nodes = kind == 1 ? n1 * (n1 + 1) / 2 : npix;
     DevBuf dval, dpos, dplane, df0, df1, ddata, dimg, dbad;
+    // species are independent: the (latency-bound, one CTA per plane) hole fill runs for a batch of
+    // planes at once, as many as fit a 48 GB budget
+    int batch = (int)std::max<int64_t>(1, std::min<int64_t>(d, (int64_t)48e9 / (int64_t)(sizeof(double) * npix)));
     PHMRF_CUDA(cudaMalloc(&dval.p, sizeof(double) * n * d));
     PHMRF_CUDA(cudaMalloc(&dpos.p, sizeof(int64_t) * 2 * n));
-    PHMRF_CUDA(cudaMalloc(&dplane.p, sizeof(double) * npix));
+    PHMRF_CUDA(cudaMalloc(&dplane.p, sizeof(double) * npix * batch));
     PHMRF_CUDA(cudaMalloc(&ddata.p, sizeof(double) * n_nodes * d));
     PHMRF_CUDA(cudaMalloc(&dbad.p, sizeof(int)));
     if (filter_mode == 0 && niter > 0) {
@@ -283,30 +286,38 @@ extern "C" int phmrf_prep_region_image(int device, const double *value, const in
     PHMRF_CUDA(cudaMemcpy(dval.p, value, sizeof(double) * n * d, cudaMemcpyHostToDevice));
     PHMRF_CUDA(cudaMemcpy(dpos.p, pos, sizeof(int64_t) * 2 * n, cudaMemcpyHostToDevice));
     PHMRF_CUDA(cudaMemset(dbad.p, 0, sizeof(int)));
-    double *plane = dplane.as<double>();
     const dim3 g2((unsigned)((n2 + 255) / 256), (unsigned)(n1 < 4096 ? n1 : 4096));
-    for (int c = 0; c < d; ++c) {
-        PHMRF_CUDA(cudaMemsetAsync(plane, 0, sizeof(double) * npix));
-        scatter_kernel<<<grid_for(n), 256>>>(dval.as<double>(), dpos.as<int64_t>(), n, d, c, start1, start2, n1, n2,
-                                             kind == 1, plane, dbad.as<int>());
-        holefill_kernel<<<1, 1024>>>(plane, npix, n1, n2, kind == 1);
-        if (kind == 1) mirror_kernel<<<grid_for(npix), 256>>>(plane, n1);
-        count_launch(kind == 1 ? 3 : 2);
-        if (filter_mode == 0 && niter > 0) {
-            float *a = df0.as<float>(), *b = df1.as<float>();
-            to_f32_kernel<<<grid_for(npix), 256>>>(plane, a, npix);
-            for (int it = 0; it < niter; ++it) {
-                diffuse_kernel<<<g2, 256>>>(a, b, n1, n2, (float)kappa, (float)gamma);
-                std::swap(a, b);
+    for (int c0 = 0; c0 < d; c0 += batch) {
+        const int nb = std::min(batch, d - c0);
+        PHMRF_CUDA(cudaMemsetAsync(dplane.p, 0, sizeof(double) * npix * nb));
+        for (int q = 0; q < nb; ++q)
+            scatter_kernel<<<grid_for(n), 256>>>(dval.as<double>(), dpos.as<int64_t>(), n, d, c0 + q, start1, start2, n1,
+                                                 n2, kind == 1, dplane.as<double>() + (int64_t)q * npix, dbad.as<int>());
+        holefill_kernel<<<nb, 1024>>>(dplane.as<double>(), npix, n1, n2, kind == 1);
+        count_launch(nb + 1);
+        for (int q = 0; q < nb; ++q) {
+            const int c = c0 + q;
+            double *plane = dplane.as<double>() + (int64_t)q * npix;
+            if (kind == 1) {
+                mirror_kernel<<<grid_for(npix), 256>>>(plane, n1);
+                count_launch();
             }
-            to_f64_kernel<<<grid_for(npix), 256>>>(a, plane, npix);
-            count_launch(niter + 2);
-        }
-        flatten_kernel<<<g2, 256>>>(plane, n1, n2, kind, d, c, ddata.as<double>());
-        count_launch();
-        if (image_out) {
-            interleave_kernel<<<grid_for(npix), 256>>>(plane, npix, d, c, dimg.as<double>());
+            if (filter_mode == 0 && niter > 0) {
+                float *a = df0.as<float>(), *b = df1.as<float>();
+                to_f32_kernel<<<grid_for(npix), 256>>>(plane, a, npix);
+                for (int it = 0; it < niter; ++it) {
+                    diffuse_kernel<<<g2, 256>>>(a, b, n1, n2, (float)kappa, (float)gamma);
+                    std::swap(a, b);
+                }
+                to_f64_kernel<<<grid_for(npix), 256>>>(a, plane, npix);
+                count_launch(niter + 2);
+            }
+            flatten_kernel<<<g2, 256>>>(plane, n1, n2, kind, d, c, ddata.as<double>());
             count_launch();
+            if (image_out) {
+                interleave_kernel<<<grid_for(npix), 256>>>(plane, npix, d, c, dimg.as<double>());
+                count_launch();
+            }
         }
         PHMRF_CUDA(cudaGetLastError());
     }
