@@ -37,6 +37,20 @@ __global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, doubl
                 a0 = fma(b0, c0, a0); a1 = fma(b1, c1, a1); a2 = fma(b2, c2, a2); a3 = fma(b3, c3, a3);
                 a4 = fma(b0, c1, a4); a5 = fma(b1, c2, a5); a6 = fma(b2, c3, a6); a7 = fma(b3, c0, a7);
             }
+        } else if (MODE == 4) {  // one multiplicand shared by four consecutive FMAs (the emission kernel's pattern)
+            double b0 = a0 * m, b1 = a1 * m, c0 = a4 * m, c1 = a5 * m, c2 = a6 * m, c3 = a7 * m;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a0 = fma(c0, b0, a0); a1 = fma(c1, b0, a1); a2 = fma(c2, b0, a2); a3 = fma(c3, b0, a3);
+                a4 = fma(c0, b1, a4); a5 = fma(c1, b1, a5); a6 = fma(c2, b1, a6); a7 = fma(c3, b1, a7);
+            }
+        } else if (MODE == 5) {  // boustrophedon order: every FMA shares one multiplicand with its predecessor
+            double b0 = a0 * m, b1 = a1 * m, c0 = a4 * m, c1 = a5 * m, c2 = a6 * m, c3 = a7 * m;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a0 = fma(c0, b0, a0); a1 = fma(c1, b0, a1); a2 = fma(c2, b0, a2); a3 = fma(c3, b0, a3);
+                a7 = fma(c3, b1, a7); a6 = fma(c2, b1, a6); a5 = fma(c1, b1, a5); a4 = fma(c0, b1, a4);
+            }
         } else if (MODE == 2) {  // exp throughput: 8 independent exps per iteration
             a0 = exp(a0 * 1e-3 - 1.0); a1 = exp(a1 * 1e-3 - 1.0); a2 = exp(a2 * 1e-3 - 1.0); a3 = exp(a3 * 1e-3 - 1.0);
             a4 = exp(a4 * 1e-3 - 1.0); a5 = exp(a5 * 1e-3 - 1.0); a6 = exp(a6 * 1e-3 - 1.0); a7 = exp(a7 * 1e-3 - 1.0);
@@ -154,7 +168,7 @@ int run_probe(int which, double *out) {
     const int grid = sms * 8, block = 256;
     float ms = 0;
     int rc = PHMRF_OK;
-    if ((which >= 0 && which <= 4) || which == 6) {
+    if ((which >= 0 && which <= 4) || which == 6 || which == 15 || which == 16) {
         PHMRF_CUDA(cudaMalloc(&buf, sizeof(double) * grid * block));
         const int iters = which == 2 ? 2000 : 4000;
         if (which == 1) {
@@ -169,12 +183,14 @@ int run_probe(int which, double *out) {
             case 3: rc = time_best([&] { dmma_kernel<false><<<grid, block>>>(buf, iters, 1.0); }, 5, &ms); break;
             case 4: rc = time_best([&] { dmma_kernel<true><<<grid, block>>>(buf, iters, 1.0); }, 5, &ms); break;
             case 6: rc = time_best([&] { dfma_kernel<3><<<grid, block>>>(buf, iters, 1e-3); }, 5, &ms); break;
+            case 15: rc = time_best([&] { dfma_kernel<4><<<grid, block>>>(buf, iters, 1e-3); }, 5, &ms); break;
+            case 16: rc = time_best([&] { dfma_kernel<5><<<grid, block>>>(buf, iters, 1e-3); }, 5, &ms); break;
         }
         count_launch(7);
         cudaFree(buf);
         if (rc != PHMRF_OK) return rc;
         const double threads = (double)grid * block;
-        if (which == 0 || which == 1 || which == 6) *out = threads * iters * 64.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (which == 0 || which == 1 || which == 6 || which == 15 || which == 16) *out = threads * iters * 64.0 * 2.0 / (ms * 1e-3) / 1e12;
         if (which == 2) *out = threads * iters * 8.0 / (ms * 1e-3) / 1e9;
         if (which == 3) *out = (threads / 32.0) * iters * 16.0 * 256.0 * 2.0 / (ms * 1e-3) / 1e12;
         if (which == 4) *out = ((threads / 32.0) * iters * 16.0 * 256.0 * 2.0 + threads * iters * 32.0 * 2.0) / (ms * 1e-3) / 1e12;
