@@ -54,3 +54,53 @@ def test_diffusion_restatement_properties():
     np.testing.assert_array_equal(po.anisotropic_diffusion(c, niter=3), c.astype(np.float32))
     # smoothing: the variance does not grow
     assert out.var() <= a.var()
+
+
+def _wavefront_fill(m, symmetric):
+    """The schedule csrc/kernels_prep.cu (holefill_kernel) uses, restated with NumPy: all cells with
+    the same t = 2i + j are updated together from a snapshot; cells below the diagonal are read
+    through their mirror and rewritten at the end."""
+    m = m.copy()
+    n1, n2 = m.shape
+    i_hi, j_hi = n1 - 2, n2 - 2
+    if i_hi < 2 or j_hi < 2:
+        return m
+    for t in range(2 * 2 + 2, 2 * i_hi + j_hi + 1):
+        snap = m.copy()
+        for i in range(2, i_hi + 1):
+            j = t - 2 * i
+            if j < (i if symmetric else 2) or j > j_hi:
+                continue
+            if snap[i, j] < po.THRESH1:
+                w = []
+                for di in (-1, 0, 1):
+                    for dj in (-1, 0, 1):
+                        if di == 0 and dj == 0:
+                            continue
+                        a, b = i + di, j + dj
+                        if symmetric and a > b:
+                            a, b = b, a
+                        w.append(snap[a, b])
+                med = np.median(w)
+                if med > po.THRESH1:
+                    m[i, j] = med
+    if symmetric:
+        iu = np.triu_indices(n1, 1)
+        m[(iu[1], iu[0])] = m[iu]
+    return m
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_wavefront_schedule_equals_the_sequential_scan(name):
+    """The GPU hole fill's 2i+j wavefront must give the reference's in-place raster-scan result."""
+    p = "prep_%s_" % name
+    mtx = G[p + "mtx"]
+    for c in range(mtx.shape[2]):
+        np.testing.assert_array_equal(_wavefront_fill(mtx[:, :, c], True), G[p + "filled"][:, :, c])
+    np.testing.assert_array_equal(_wavefront_fill(G[p + "rect"], False), G[p + "rect_filled"])
+    rng = np.random.default_rng(7)   # sparse image: long fill cascades along rows and across the diagonal
+    s = rng.random((31, 31)) * (rng.random((31, 31)) < 0.45)
+    s = np.triu(s) + np.triu(s, 1).T
+    np.testing.assert_array_equal(_wavefront_fill(s, True), po.near_interpolation1(s.copy()))
+    r = rng.random((19, 27)) * (rng.random((19, 27)) < 0.5)
+    np.testing.assert_array_equal(_wavefront_fill(r, False), po.near_interpolation1a(r.copy()))
