@@ -25,8 +25,10 @@ using namespace estep;
 namespace {
 
 constexpr int kConsumers = 4;
-constexpr int kProducers = 8;
-constexpr int kPipeThreads = 32 * (kConsumers + kProducers);
+// producer warps per CTA: 8 (two per consumer) for the big accumulator tiles, 12 when the state x
+// feature tile is small enough that the consumers hardly load the FP64 pipe and a producer fits
+// 128 registers
+constexpr int pipe_threads(int P) { return 32 * (kConsumers + P); }
 constexpr int kTileNodes = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,8 +93,9 @@ __device__ __forceinline__ void write_yd_chunks(double *Yrow, const double (&x)[
 }
 
 // NK8 = number of 8-state tiles (K <= 8*NK8).
-template <int D, int NK8>
-__global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a) {
+template <int D, int NK8, int P>
+__global__ void __launch_bounds__(pipe_threads(P), 1) estep_mma_kernel(EstepArgs a) {
+    constexpr int kProducers = P;
     constexpr int F = n_stat_features(D);
     constexpr int NT = (F + 7) / 8;        // 8-feature tiles
     constexpr int KP = 8 * NK8, FP = 8 * NT;
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
 
     if (warp >= kConsumers) {
         // =============================== PRODUCER ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
+        if constexpr (P == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
         const int p = warp - kConsumers;
         double *slot = smem + (size_t)p * slot_doubles;
         double *Prow = slot + lane * RSP;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
         }
     } else {
         // =============================== CONSUMER ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        if constexpr (P == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         const int c = warp;
         const int g = lane >> 2, t = lane & 3;
         double acc[NK8][NT][2];
@@ -369,29 +372,40 @@ __global__ void __launch_bounds__(kPipeThreads, 1) estep_mma_kernel(EstepArgs a)
     for (int e0 = threadIdx.x; e0 < KF + 3; e0 += blockDim.x) out[e0] = red[e0];
 }
 
-template <int D, int NK8>
-int launch_mma(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
+template <int D, int NK8, int P>
+int launch_mma_p(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     constexpr int F = n_stat_features(D);
     constexpr int NT = (F + 7) / 8;
-    if (NK8 * NT * 2 > 64) return PHMRF_OK;  // accumulator tiles would not fit the consumer's registers
     constexpr int RSP = 8 * NK8 + 4, RSY = 8 * NT + 4;
     const size_t slot = (size_t)kTileNodes * (RSP + RSY) * sizeof(double);
-    size_t smem = kProducers * slot + 2 * kProducers * sizeof(uint64_t);
+    size_t smem = P * slot + 2 * P * sizeof(uint64_t);
     const size_t red_bytes = ((size_t)a.K * F + 3) * sizeof(double);
     if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return PHMRF_OK;
     const int64_t n_tiles = (a.n + kTileNodes - 1) / kTileNodes;
-    int64_t want = (n_tiles + kProducers - 1) / kProducers;
+    int64_t want = (n_tiles + P - 1) / P;
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
-    auto kern = estep_mma_kernel<D, NK8>;
+    auto kern = estep_mma_kernel<D, NK8, P>;
     PHMRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kPipeThreads, smem, s>>>(a);
+    kern<<<grid, pipe_threads(P), smem, s>>>(a);
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     *handled = true;
     return launch_estep_finalize(a.partials, grid, a.K, D, a.stats_out, s);
 }
 
+template <int D, int NK8>
+int launch_mma(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
+    constexpr int F = n_stat_features(D);
+    constexpr int NT = (F + 7) / 8;
+    if constexpr (NK8 * NT * 2 > 64) {
+        return PHMRF_OK;  // accumulator tiles would not fit the consumer's registers
+    } else if constexpr (NK8 * NT <= 12 && NK8 <= 3) {
+        return launch_mma_p<D, NK8, 12>(a, sm_count, s, handled);
+    } else {
+        return launch_mma_p<D, NK8, 8>(a, sm_count, s, handled);
+    }
+}
 template <int D>
 int launch_pipe_d(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     switch ((a.K + 7) / 8) {
