@@ -164,6 +164,8 @@ CASES = [
     (45, 2, 1, 3, 1.0, True),      # single state
     (60, 5, 20, 3, 1.0, False),    # general (non-Potts) compatibility matrix
     (60, 3, 6, 0, 1.0, False),
+    (40, 3, 5, 3, -0.8, True),     # repulsive coupling: slot factors below 1
+    (33, 9, 30, 0, 1.3, True),     # unweighted estimate on the headline shape
 ]
 
 
