@@ -203,13 +203,15 @@ int phmrf_prep_normalise(int device, double *x, int64_t n, int d, double *x_min,
  *      (utility.py:603-659; executed as a 2i+j wavefront, which preserves every dependency);
  *   3. filter_mode 0: Perona-Malik anisotropic diffusion, niter steps, conduction
  *      exp(-(delta/kappa)^2), step gamma, float32 like medpy's implementation (the call at
- *      utility.py:1566-1573); any other filter_mode: no filter;
+ *      utility.py:1566-1573); filter_mode 2 with sigma > 0: scipy.ndimage.gaussian_filter(plane, sigma)
+ *      (float64, mode 'reflect', truncate 4; utility.py:1585-1589); any other combination: no filter
+ *      (filter_mode 1, the skimage bilateral filter, is not built);
  *   4. nodes in the reference's order: the upper triangle row by row (kind 1) or the whole block
  *      (kind 0) -> data_out [n_nodes, d] row-major (utility.py:2295-2329, 2368-2400).
  * image_out (nullable) receives the filtered image [n1, n2, d]. */
 int phmrf_prep_region_image(int device, const double *value, const int64_t *pos, int64_t n, int d, int kind,
                             int64_t start1, int64_t start2, int64_t n1, int64_t n2, int filter_mode, int niter,
-                            double kappa, double gamma, double *data_out, double *image_out);
+                            double kappa, double gamma, double sigma, double *data_out, double *image_out);
 
 /* ------------------------------------------------------------------ probes ------------ */
 

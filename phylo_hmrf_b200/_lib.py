@@ -74,7 +74,7 @@ SIGNATURES = {
                                        C.c_int]),
     "phmrf_prep_region_image": (C.c_int, [C.c_int, _c_double_p, _c_int64_p, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                           C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double,
-                                          _c_double_p, _c_double_p]),
+                                          C.c_double, _c_double_p, _c_double_p]),
     "phmrf_probe_fp64_tflops": (C.c_int, [C.c_int, _c_double_p]),
     "phmrf_probe": (C.c_int, [C.c_int, C.c_int, _c_double_p]),
 }

@@ -4,6 +4,7 @@
 // 2295-2329, 2368-2400.  One-shot per data set and HBM-/latency-bound; everything runs on the device
 // so that a 10 kb chr1 image (6.2e8 pixels per species) never exists on the host.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -174,6 +175,31 @@ __global__ void __launch_bounds__(256) diffuse_kernel(const float *__restrict__ 
     }
 }
 
+// One axis of scipy.ndimage.gaussian_filter (order 0, mode 'reflect'): symmetric correlation in
+// scipy's summation order (NI_Correlate1D: centre tap first, then the pairs from the outermost in),
+// separate multiply and add.
+__global__ void __launch_bounds__(256) gauss1d_kernel(const double *__restrict__ in, double *__restrict__ out, int64_t n1,
+                                                      int64_t n2, int axis, const double *__restrict__ w, int lw) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const int64_t len = axis == 0 ? n1 : n2, stride = axis == 0 ? n2 : 1;
+    for (int64_t i = blockIdx.y; i < n1; i += gridDim.y) {
+        const int64_t pos = axis == 0 ? i : j;
+        const double *line = in + (axis == 0 ? j : i * n2);
+        auto at = [&](int64_t k) {  // 'reflect': d c b a | a b c d | d c b a
+            const int64_t per = 2 * len;
+            k %= per;
+            if (k < 0) k += per;
+            if (k >= len) k = per - 1 - k;
+            return line[k * stride];
+        };
+        double tmp = __dmul_rn(at(pos), w[lw]);
+        for (int jj = -lw; jj < 0; ++jj)
+            tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(pos + jj), at(pos - jj)), w[jj + lw]));
+        out[i * n2 + j] = tmp;
+    }
+}
+
 // node order: upper triangle row by row (kind 1) or the whole block (kind 0)
 __global__ void flatten_kernel(const double *__restrict__ plane, int64_t n1, int64_t n2, int kind, int d, int c,
                                double *__restrict__ data) {
@@ -260,7 +286,8 @@ extern "C" int phmrf_prep_normalise(int device, double *x, int64_t n, int d, dou
 
 extern "C" int phmrf_prep_region_image(int device, const double *value, const int64_t *pos, int64_t n, int d, int kind,
                                        int64_t start1, int64_t start2, int64_t n1, int64_t n2, int filter_mode,
-                                       int niter, double kappa, double gamma, double *data_out, double *image_out) {
+                                       int niter, double kappa, double gamma, double sigma, double *data_out,
+                                       double *image_out) {
     if (!value || !pos || n <= 0 || d <= 0 || n1 <= 0 || n2 <= 0 || !data_out || (kind != 0 && kind != 1) ||
         (kind == 1 && (n1 != n2 || start1 != start2))) {
         set_error("phmrf_prep_region_image: bad argument");
@@ -269,7 +296,23 @@ extern "C" int phmrf_prep_region_image(int device, const double *value, const in
     PHMRF_CUDA(cudaSetDevice(device));
     const int64_t npix = n1 * n2;
     const int64_t n_nodes = kind == 1 ? n1 * (n1 + 1) / 2 : npix;
-    DevBuf dval, dpos, dplane, df0, df1, ddata, dimg, dbad;
+    DevBuf dval, dpos, dplane, df0, df1, ddata, dimg, dbad, dgw, dtmp;
+    int lw = 0;
+    if (filter_mode == 2 && sigma > 0) {
+        // scipy.ndimage._filters._gaussian_kernel1d: radius int(4 sigma + 0.5), exp(-x^2 / (2 sigma^2)) normalised
+        lw = (int)(4.0 * sigma + 0.5);
+        std::vector<double> gw(2 * (size_t)lw + 1);
+        const double s2 = sigma * sigma;
+        double tot = 0.0;
+        for (int x = -lw; x <= lw; ++x) {
+            gw[x + lw] = std::exp(-0.5 / s2 * ((double)x * (double)x));
+            tot += gw[x + lw];
+        }
+        for (auto &v : gw) v /= tot;
+        PHMRF_CUDA(cudaMalloc(&dgw.p, sizeof(double) * gw.size()));
+        PHMRF_CUDA(cudaMemcpy(dgw.p, gw.data(), sizeof(double) * gw.size(), cudaMemcpyHostToDevice));
+        PHMRF_CUDA(cudaMalloc(&dtmp.p, sizeof(double) * npix));
+    }
     // species are independent: the (latency-bound, one CTA per plane) hole fill runs for a batch of
     // planes at once, as many as fit a 48 GB budget
     int batch = (int)std::max<int64_t>(1, std::min<int64_t>(d, (int64_t)48e9 / (int64_t)(sizeof(double) * npix)));
@@ -311,6 +354,11 @@ extern "C" int phmrf_prep_region_image(int device, const double *value, const in
                 }
                 to_f64_kernel<<<grid_for(npix), 256>>>(a, plane, npix);
                 count_launch(niter + 2);
+            }
+            if (filter_mode == 2 && sigma > 0) {  // axis 0 then axis 1, like scipy
+                gauss1d_kernel<<<g2, 256>>>(plane, dtmp.as<double>(), n1, n2, 0, dgw.as<double>(), lw);
+                gauss1d_kernel<<<g2, 256>>>(dtmp.as<double>(), plane, n1, n2, 1, dgw.as<double>(), lw);
+                count_launch(2);
             }
             flatten_kernel<<<g2, 256>>>(plane, n1, n2, kind, d, c, ddata.as<double>());
             count_launch();

@@ -84,7 +84,7 @@ def _normalise(x1, x_min, x_max, log1p, device):
     return x, vec1, lo.value, hi.value
 
 
-def _region_image(value, pos, kind, filter_mode, filter_param1, filter_param2, want_image, device):
+def _region_image(value, pos, kind, filter_mode, filter_param1, filter_param2, want_image, device, sigma=0.0):
     value = as_f64(value)
     pos = np.ascontiguousarray(np.asarray(pos), dtype=np.int64)
     if value.ndim != 2 or pos.shape != (value.shape[0], 2) or value.shape[0] == 0:
@@ -99,18 +99,19 @@ def _region_image(value, pos, kind, filter_mode, filter_param1, filter_param2, w
     else:          # utility.py:2341-2346
         n1, n2 = e1 - s1 + 1, e2 - s2 + 1
         n_nodes = n1 * n2
-    if filter_mode == 0:
+    niter, kappa, mode = 0, 50.0, -1
+    if filter_mode == 0:    # anisotropic diffusion (utility.py:1566-1573)
         niter, kappa = (10, 50.0) if filter_param1 < 0 else (int(filter_param1), float(filter_param2))
-    elif filter_mode in (1, 2):
-        raise NotImplementedError("filter_mode 1 (bilateral) and 2 (Gaussian) are not built; the reference's "
-                                  "pipeline uses filter_mode 0 (utility.py:411-412)")
-    else:
-        niter, kappa = 0, 50.0
+        mode = 0
+    elif filter_mode == 1:  # skimage denoise_bilateral (utility.py:1575-1582)
+        raise NotImplementedError("filter_mode 1 (bilateral filter) is not built")
+    elif sigma > 0:         # any other mode: Gaussian blur when sigma > 0 (utility.py:1584-1589)
+        mode = 2
     data1 = np.empty((n_nodes, d), dtype=np.float64)
     mtx1 = np.empty((n1, n2, d), dtype=np.float64) if want_image else None
     check(_lib.lib().phmrf_prep_region_image(int(device), dptr(value), pos.ctypes.data_as(C.POINTER(C.c_int64)),
-                                             value.shape[0], d, kind, s1, s2, n1, n2, 0 if filter_mode == 0 else -1,
-                                             niter, kappa, 0.1, dptr(data1),
+                                             value.shape[0], d, kind, s1, s2, n1, n2, mode,
+                                             niter, kappa, 0.1, float(sigma), dptr(data1),
                                              dptr(mtx1) if want_image else None))
     return data1, mtx1, (s1, s2), (n1, n2)
 
@@ -120,7 +121,7 @@ def write_matrix_image_Ctrl_unsym1(value, pos, output_filename1, output_filename
     """utility.py:1519-1598 (diagonal region): image, hole fill, anisotropic diffusion, upper-triangle
     node list and its edge list.  Returns (data1, mtx1, pos_idx, edge_list)."""
     data1, mtx1, (s1, _), (n1, _) = _region_image(value, pos, 1, filter_mode, filter_param1, filter_param2,
-                                                  want_image, device)
+                                                  want_image, device, sigma)
     ii, jj = np.triu_indices(n1)
     pos_idx = np.stack([ii, jj], axis=1) + s1
     edge_list = _edges(data1, 1, n1, n1, num_neighbor, device)
@@ -132,7 +133,7 @@ def write_matrix_image_Ctrl_sym1(value, pos, output_filename1, output_filename2,
                                  filter_mode, filter_param1, filter_param2, device=0, want_image=True):
     """utility.py:1704-1783 (off-diagonal block).  Returns (data1, mtx1, pos_idx, edge_list)."""
     data1, mtx1, (s1, s2), (n1, n2) = _region_image(value, pos, 0, filter_mode, filter_param1, filter_param2,
-                                                    want_image, device)
+                                                    want_image, device, sigma)
     ii, jj = np.meshgrid(np.arange(n1), np.arange(n2), indexing="ij")
     pos_idx = np.stack([ii.ravel() + s1, jj.ravel() + s2], axis=1)
     edge_list = _edges(data1, 0, n1, n2, num_neighbor, device)

@@ -115,3 +115,17 @@ def test_rejects_pairs_outside_the_window_and_unbuilt_filters(util):
         util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0, 1, 1, -1, -1)
     with pytest.raises(ValueError):
         util.normalize_feature(np.zeros((0, 3)), -1, -1)
+
+
+@pytest.mark.parametrize("sigma", [0.25, 1.5, 7.0])
+def test_gaussian_filter_mode_matches_scipy(util, sigma):
+    """filter_mode 2 (utility.py:1584-1589): scipy.ndimage.gaussian_filter on the hole-filled image;
+    sigma = 7 makes the kernel radius (28) exceed the 20-bin window, i.e. repeated reflections."""
+    val, pos = _random_region(21, 20, 2, 0.7)
+    ref = po.image_pipeline_diag(val, pos, filter_mode=2, sigma=sigma)
+    got = util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, sigma, 1, 2, -1, -1)
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(got[0], ref[0], rtol=1e-13, atol=1e-300)
+    # sigma = 0 leaves the image unfiltered (utility.py:1585)
+    none = util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0.0, 1, 2, -1, -1)
+    np.testing.assert_array_equal(none[1], po.image_pipeline_diag(val, pos, filter_mode=-1)[1])
