@@ -104,3 +104,16 @@ def test_wavefront_schedule_equals_the_sequential_scan(name):
     np.testing.assert_array_equal(_wavefront_fill(s, True), po.near_interpolation1(s.copy()))
     r = rng.random((19, 27)) * (rng.random((19, 27)) < 0.5)
     np.testing.assert_array_equal(_wavefront_fill(r, False), po.near_interpolation1a(r.copy()))
+
+
+def test_host_side_argument_checks_need_no_gpu():
+    """The utility.py mirrors validate their arguments before any device call."""
+    from phylo_hmrf_b200 import utility
+    val = np.ones((3, 2))
+    pos = np.array([[0, 0], [0, 1], [1, 1]], dtype=np.int64)
+    with pytest.raises(NotImplementedError):   # bilateral filter (skimage) is not built
+        utility.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0.0, 1, 1, -1, -1)
+    with pytest.raises(ValueError):
+        utility.write_matrix_image_Ctrl_unsym1(val, pos[:2], "", "", 8, 0.0, 1, 0, 5, 50)
+    with pytest.raises(ValueError):
+        utility.normalize_feature(np.zeros((0, 3)), -1, -1)
