@@ -1,7 +1,7 @@
 // Phase B, warp-specialised pipeline (the fast path for the reference's own model shape:
 // Potts compatibility, <= 8 neighbour slots, K <= 40 states).
 //
-// One CTA per SM, 16 warps:
+// One CTA per SM, 4 + P warps (P = 8, or 12 for small accumulator tiles):
 //   warps 0-3   CONSUMERS (one per SM sub-partition): hold the K x F sufficient-statistic
 //               accumulators and do nothing but  S[k][f] += e[n][k] * y[n][f].  This is a
 //               dense (K x n)(n x F) FP64 product, issued as DMMA.8x8x4 (mma.sync m8n8k4
@@ -11,8 +11,9 @@
 //               shared-memory wavefronts than the DFMA formulation it replaced (ncu: LSU
 //               wavefronts were at 72 % of peak and the sub-partition issue port was the
 //               limiter, see profiles/r1_history.md).
-//   warps 4-11  PRODUCERS: the latency-bound per-node work -- neighbour gather, soft-max
-//               terms, cost scalars, feature row -- for tiles of 32 nodes, one lane per node.
+//   warps 4..   PRODUCERS: the per-node work -- neighbour gather (per-slot factors exp(beta*w)
+//               are precomputed per region), soft-max terms, cost scalars, feature row -- for
+//               tiles of 32 nodes, one lane per node.
 // A producer owns one shared-memory slot (32 P rows + 32 Y rows); producer p feeds consumer
 // p % 4 through a full/empty mbarrier pair.
 // Same arithmetic as kernels_b.cu (reference: phylo_hmrf.py:311-314, 334-468).
