@@ -139,3 +139,60 @@ def write_matrix_image_Ctrl_sym1(value, pos, output_filename1, output_filename2,
     edge_list = _edges(data1, 0, n1, n2, num_neighbor, device)
     _maybe_write(edge_list, output_filename2)
     return data1, mtx1, pos_idx, edge_list
+
+
+def select_valuesPosition1_2(position, x, output_filename, position1, position2, position1a, position2a, resolution,
+                             border_type=0):
+    """utility.py:1331-1364: rows of the aligned matrix whose bin pair lies in the region
+    [position1, position2] x [position1a, position2a] (genomic coordinates).  Host NumPy."""
+    position = np.asarray(position)
+    if border_type == 0:
+        x1, x2 = position[:, 0] * resolution, (position[:, 1] + 1) * resolution
+        b = (x1 >= position1) & (x1 <= position2) & (x2 >= position1a) & (x2 <= position2a)
+    elif border_type == 1:
+        x1, x2 = position[:, 0] * resolution, (position[:, 1] + 1) * resolution
+        b = (x1 >= position1) & (x2 <= position2)
+    else:
+        x1, x2 = position[:, 0] * resolution, position[:, 1] * resolution
+        b = (x1 >= position1) & (x1 < position2) & (x2 >= position1a) & (x2 < position2a)
+    b1 = np.where(b)[0]
+    if output_filename != "":
+        import pandas as pd
+        n_fields = 3 + x.shape[1]
+        data2 = pd.DataFrame(columns=range(n_fields))
+        for i in range(3):
+            data2[i] = position[b1, i]
+        for i in range(3, n_fields):
+            data2[i] = x[b1, i - 3]
+        data2.to_csv(output_filename, index=False, sep='\t')
+    return x[b1, :], b1
+
+
+def load_data_chromosome_sub3(region_id, chrom_id, region_list, x, position, param_vec, m_queue, device=0):
+    """utility.py:470-534: one region of a chromosome -> (region_id, samples, len_vec entry, edge list) on
+    ``m_queue`` (anything with ``put``).  The image pipeline and the edge list run on the GPU."""
+    t_position1 = region_list[region_id]
+    position1, position2, position1a, position2a = t_position1[0], t_position1[1], t_position1[2], t_position1[3]
+    region_id1 = t_position1[6]
+    resolution, num_neighbor, filter_mode, filter_param1, filter_param2, sigma = param_vec[:6]
+    type_id1 = 1 if (position1 == position1a and position2 == position2a) else 0
+    x1, idx = select_valuesPosition1_2(position, x, "", position1, position2, position1a, position2a, resolution, 0)
+    t_position = np.asarray(position)[idx, :]
+    if type_id1 == 1:
+        x1, _, _, edge_list_1 = write_matrix_image_Ctrl_unsym1(x1, t_position, "", "", num_neighbor, sigma, 1,
+                                                               filter_mode, filter_param1, filter_param2,
+                                                               device=device, want_image=False)
+        start_region1 = start_region2 = np.min(t_position)          # utility.py:516-517
+        lo = int(min(t_position[:, 0].min(), t_position[:, 1].min()))
+        n1 = n2 = int(max(t_position[:, 0].max(), t_position[:, 1].max())) - lo + 1
+    else:
+        x1, _, _, edge_list_1 = write_matrix_image_Ctrl_sym1(x1, t_position, "", "", num_neighbor, sigma, 0,
+                                                             filter_mode, filter_param1, filter_param2,
+                                                             device=device, want_image=False)
+        temp1 = np.min(t_position, 0)
+        start_region1, start_region2 = temp1[0], temp1[1]
+        n1 = int(t_position[:, 0].max() - t_position[:, 0].min()) + 1
+        n2 = int(t_position[:, 1].max() - t_position[:, 1].min()) + 1
+    t_lenvec = [x1.shape[0], n1, n2, start_region1, start_region2, region_id1, type_id1, chrom_id]
+    m_queue.put((region_id, x1, t_lenvec, edge_list_1))
+    return True

@@ -1,6 +1,6 @@
 """Generate tests/golden/prep_cases.npz from the reference's own preprocessing functions
 (utility.py: normalize_feature, write_matrix_image_v1, near_interpolation1, near_interpolation1a,
-write_matrix_array_v1), executed in memory through ref_loader.  Build container only.
+write_matrix_array_v1; select_valuesPosition1_2 -> select_cases.npz), executed in memory through ref_loader.  Build container only.
 
 usage: python tests/golden/make_golden_prep.py
 """
@@ -28,9 +28,32 @@ def contact_triples(rng, W, d, start, fill):
     return val, pos
 
 
+def make_select_cases():
+    """utility.py:1331-1364 select_valuesPosition1_2 on a 30-bin triangle, the three border types."""
+    util = ref_loader.load_utility(["select_valuesPosition1_2"])
+    rng = np.random.default_rng(3)
+    W = 30
+    ii, jj = np.triu_indices(W)
+    position = np.stack([ii + 5, jj + 5, np.arange(len(ii)) + 1000], axis=1).astype(np.int64)
+    x = rng.random((len(ii), 3))
+    out = {"position": position, "x": x}
+    res = 10000
+    cases = [(0, 80000, 250000, 80000, 250000), (0, 60000, 150000, 200000, 330000),
+             (1, 80000, 250000, 80000, 250000), (2, 80000, 250000, 100000, 300000)]
+    for k, (bt, p1, p2, p1a, p2a) in enumerate(cases):
+        xs, b1 = util["select_valuesPosition1_2"](position, x, "", p1, p2, p1a, p2a, res, bt)
+        out["sel%d_args" % k] = np.array([bt, p1, p2, p1a, p2a, res])
+        out["sel%d_idx" % k] = b1
+        out["sel%d_x" % k] = xs
+    path = os.path.join(HERE, "select_cases.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not present")
+    make_select_cases()
     util = ref_loader.load_utility(["normalize_feature", "write_matrix_image_v1", "near_interpolation1",
                                     "near_interpolation1a", "write_matrix_array_v1"])
     util["THRESH1"] = 1e-05

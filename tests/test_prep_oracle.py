@@ -117,3 +117,52 @@ def test_host_side_argument_checks_need_no_gpu():
         utility.write_matrix_image_Ctrl_unsym1(val, pos[:2], "", "", 8, 0.0, 1, 0, 5, 50)
     with pytest.raises(ValueError):
         utility.normalize_feature(np.zeros((0, 3)), -1, -1)
+
+
+def test_select_values_position_against_reference_fixture():
+    from phylo_hmrf_b200 import utility
+    S = np.load(os.path.join(os.path.dirname(__file__), "golden", "select_cases.npz"))
+    for k in range(4):
+        bt, p1, p2, p1a, p2a, res = (int(v) for v in S["sel%d_args" % k])
+        xs, idx = utility.select_valuesPosition1_2(S["position"], S["x"], "", p1, p2, p1a, p2a, res, bt)
+        np.testing.assert_array_equal(idx, S["sel%d_idx" % k])
+        np.testing.assert_array_equal(xs, S["sel%d_x" % k])
+
+
+def test_region_loader_glue(monkeypatch):
+    """utility.load_data_chromosome_sub3 (utility.py:470-534) with the two GPU-backed image builders
+    replaced by oracle stand-ins: region typing, window shape, start bins and the queue tuple."""
+    from phylo_hmrf_b200 import utility
+
+    def fake_unsym(value, pos, f1, f2, nn, sigma, type_id, fm, fp1, fp2, device=0, want_image=True):
+        data1, mtx1, pos_idx, _ = po.image_pipeline_diag(value, pos[:, :2], filter_mode=-1)
+        return data1, None, pos_idx, np.zeros((1, 3))
+
+    def fake_sym(value, pos, f1, f2, nn, sigma, type_id, fm, fp1, fp2, device=0, want_image=True):
+        return value.copy(), None, pos[:, :2].copy(), np.zeros((2, 3))
+
+    monkeypatch.setattr(utility, "write_matrix_image_Ctrl_unsym1", fake_unsym)
+    monkeypatch.setattr(utility, "write_matrix_image_Ctrl_sym1", fake_sym)
+    S = np.load(os.path.join(os.path.dirname(__file__), "golden", "select_cases.npz"))
+    position, x = S["position"], S["x"]
+    region_list = [[80000, 250000, 80000, 250000, 0, 0, 7, 0],      # diagonal block
+                   [60000, 150000, 200000, 330000, 0, 0, 8, 1]]     # off-diagonal block
+
+    class Q:
+        def put(self, item):
+            self.item = item
+
+    q = Q()
+    assert utility.load_data_chromosome_sub3(0, 21, region_list, x, position, [10000, 8, -1, -1, -1, 0.0], q)
+    rid, samples, lenvec, edges = q.item
+    idx = S["sel0_idx"]
+    lo, hi = position[idx, :2].min(), position[idx, :2].max()
+    W = hi - lo + 1
+    assert rid == 0 and samples.shape == (W * (W + 1) // 2, 3)
+    assert lenvec == [samples.shape[0], W, W, np.min(position[idx]), np.min(position[idx]), 7, 1, 21]
+    assert utility.load_data_chromosome_sub3(1, 21, region_list, x, position, [10000, 8, -1, -1, -1, 0.0], q)
+    rid, samples, lenvec, edges = q.item
+    idx = S["sel1_idx"]
+    p = position[idx]
+    assert rid == 1 and lenvec[1:] == [p[:, 0].max() - p[:, 0].min() + 1, p[:, 1].max() - p[:, 1].min() + 1,
+                                       p[:, 0].min(), p[:, 1].min(), 8, 0, 21]
