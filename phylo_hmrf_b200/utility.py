@@ -86,9 +86,10 @@ def _normalise(x1, x_min, x_max, log1p, device):
 
 def _region_image(value, pos, kind, filter_mode, filter_param1, filter_param2, want_image, device, sigma=0.0):
     value = as_f64(value)
-    pos = np.ascontiguousarray(np.asarray(pos), dtype=np.int64)
-    if value.ndim != 2 or pos.shape != (value.shape[0], 2) or value.shape[0] == 0:
-        raise ValueError("value must be [n, d] and pos [n, 2]")
+    pos = np.asarray(pos)
+    if value.ndim != 2 or pos.ndim != 2 or pos.shape[0] != value.shape[0] or pos.shape[1] < 2 or value.shape[0] == 0:
+        raise ValueError("value must be [n, d] and pos [n, >=2] (bin pair in the first two columns)")
+    pos = np.ascontiguousarray(pos[:, :2], dtype=np.int64)  # utility.py:2204-2222 reads columns 0 and 1 only
     d = value.shape[1]
     s1, s2 = int(pos[:, 0].min()), int(pos[:, 1].min())
     e1, e2 = int(pos[:, 0].max()), int(pos[:, 1].max())

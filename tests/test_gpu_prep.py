@@ -129,3 +129,32 @@ def test_gaussian_filter_mode_matches_scipy(util, sigma):
     # sigma = 0 leaves the image unfiltered (utility.py:1585)
     none = util.write_matrix_image_Ctrl_unsym1(val, pos, "", "", 8, 0.0, 1, 2, -1, -1)
     np.testing.assert_array_equal(none[1], po.image_pipeline_diag(val, pos, filter_mode=-1)[1])
+
+
+def test_region_loader_end_to_end(util):
+    """utility.load_data_chromosome_sub3 (utility.py:470-534) through the GPU image pipeline, against the
+    oracle composition: select -> image -> hole fill -> diffusion -> node list; len_vec entry; edge list."""
+    rng = np.random.default_rng(12)
+    W = 40
+    ii, jj = np.triu_indices(W)
+    keep = rng.random(len(ii)) < 0.7
+    ii, jj = ii[keep], jj[keep]
+    position = np.stack([ii + 3, jj + 3, np.arange(len(ii))], axis=1).astype(np.int64)
+    x = np.log1p(rng.gamma(2.0, 3.0, size=(len(ii), 3)))
+    res = 10000
+    region_list = [[100000, 300000, 100000, 300000, 0, 0, 5, 0]]
+
+    class Q:
+        def put(self, item):
+            self.item = item
+
+    q = Q()
+    assert util.load_data_chromosome_sub3(0, 21, region_list, x, position, [res, 8, 0, 5, 50, 0.0], q)
+    rid, samples, lenvec, edges = q.item
+    xs, idx = util.select_valuesPosition1_2(position, x, "", 100000, 300000, 100000, 300000, res, 0)
+    ref = po.image_pipeline_diag(xs, position[idx, :2], filter_mode=0, niter=5, kappa=50, gamma=0.1)
+    np.testing.assert_allclose(samples, ref[0], rtol=2e-5, atol=2e-6)
+    n1 = ref[1].shape[0]
+    assert rid == 0 and lenvec == [ref[0].shape[0], n1, n1, position[idx].min(), position[idx].min(), 5, 1, 21]
+    from phylo_hmrf_b200 import utility
+    assert edges.shape == (utility._lib.lib().phmrf_grid_edge_count(1, n1, n1, 8), 3)
