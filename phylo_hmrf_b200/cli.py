@@ -1,8 +1,9 @@
 """Command line of the reference (`python phylo_hmrf.py ...`, phylo_hmrf.py:1531-1760) over the
 re-hosted model: same option names and code defaults, same cache files, same
-`.mat` result.  Raw Hi-C loading / image filtering (utility.py) is not re-hosted:
-run with `--reload 1` on the `data.*.npy` / `edgelist.*.npy` / `lenvec.*.txt` caches the
-reference writes (phylo_hmrf.py:1697-1704)."""
+`.mat` result.  `--reload 1` reads the `data.*.npy` / `edgelist.*.npy` / `lenvec.*.txt` caches
+(phylo_hmrf.py:1676-1690); otherwise the species' Hi-C text files are aligned and preprocessed
+(`phylo_hmrf_b200.loader`, image pipeline on the GPU) and the caches are written
+(phylo_hmrf.py:1692-1704)."""
 from __future__ import annotations
 
 import os
@@ -36,8 +37,33 @@ def _read_table(path, cast):
         return [[cast(v) for v in line.split('\t')] for line in f if line.strip()]
 
 
+def _load_raw(opts, data_path, resolution, device):
+    """phylo_hmrf.py:1622-1695: species / path lists, chromosome list, the common x_max (median over
+    chromosomes and species of the largest contact value), then utility.load_data_chromosome2."""
+    from . import loader
+    with open("%s/species_name.1.txt" % data_path) as f:
+        species = [line.strip() for line in f if line.strip()]
+    with open("%s/path_list.txt" % data_path) as f:
+        filename_list = [line.strip() for line in f if line.strip()]
+    chromvec = str(opts.chromvec)
+    chrom_vec = list(range(1, 23)) if chromvec == "-1" else [int(c) for c in chromvec.split(',')]
+    ref_filename = "%s/%s.chrom.sizes" % (data_path, str(opts.ref_species))
+    qfile = 'chrom_quantile_test.txt'
+    if int(opts.quantile) == 0 and os.path.exists(qfile):
+        m_values = np.atleast_2d(np.loadtxt(qfile, delimiter='\t'))[:, 6]
+    else:
+        m_vec_list = loader.quantile_contact_vec(chrom_vec, resolution, ref_filename, filename_list, species)
+        np.savetxt(qfile, m_vec_list, fmt='%.4f', delimiter='\t')
+        m_values = m_vec_list[:, 6]
+    x_max, x_min = float(np.median(m_values)), 0
+    return loader.load_data_chromosome2(chrom_vec, x_max, x_min, resolution, int(opts.num_neighbor),
+                                        int(opts.filter_mode), float(opts.filter_sigma), int(opts.dtype),
+                                        ref_filename, filename_list, species, data_path, str(opts.annotation),
+                                        device=device)
+
+
 def run(opts, device=0):
-    """phylo_hmrf.py:1570-1749 for `--reload 1`.  Returns the dict written to the `.mat` file."""
+    """phylo_hmrf.py:1570-1749.  Returns the dict written to the `.mat` file."""
     import scipy.io
     from .hmrf import phyloHMRF
     run_id, K = int(opts.run_id), int(opts.num_states)
@@ -50,12 +76,19 @@ def run(opts, device=0):
     stem = "%dKb.observed.%d" % (resolution // 1000, run_id)
     f1, f2, f3 = ("%s/data.%s.npy" % (output_path, stem), "%s/edgelist.%s.npy" % (output_path, stem),
                   "%s/lenvec.%s.txt" % (output_path, stem))
-    if int(opts.reload) != 1 or not all(os.path.exists(f) for f in (f1, f2, f3)):
-        raise SystemExit("raw Hi-C loading is not re-hosted (SURVEY 8 f-4): run with --reload 1 and the cache files "
-                         "%s, %s, %s in --output" % (f1, f2, f3))
-    samples = np.load(f1)
-    edge_list_vec = list(np.load(f2, allow_pickle=True))
-    len_vec = np.atleast_2d(np.loadtxt(f3, dtype='int32', delimiter='\t')).tolist()
+    if int(opts.reload) == 1 and all(os.path.exists(f) for f in (f1, f2, f3)):
+        samples = np.load(f1)
+        edge_list_vec = list(np.load(f2, allow_pickle=True))
+        len_vec = np.atleast_2d(np.loadtxt(f3, dtype='int32', delimiter='\t')).tolist()
+    else:   # phylo_hmrf.py:1630-1706: align the species' contact files, build the regions, write the caches
+        samples, len_vec, edge_list_vec = _load_raw(opts, data_path, resolution, device)
+        os.makedirs(output_path, exist_ok=True)
+        np.save(f1, samples)
+        ev = np.empty(len(edge_list_vec), dtype=object)
+        for i, e in enumerate(edge_list_vec):
+            ev[i] = e
+        np.save(f2, ev, allow_pickle=True)
+        np.savetxt(f3, np.asarray(len_vec), fmt='%d', delimiter='\t')
     if int(opts.method_mode) != 1:
         raise SystemExit("method_mode 1 (Phylo-HMRF) is the only mode of the reference's run()")
     model = phyloHMRF(n_components=K, run_id=run_id, n_samples=samples.shape[0], n_features=samples.shape[-1],

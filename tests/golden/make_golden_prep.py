@@ -50,10 +50,72 @@ def make_select_cases():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def write_loader_inputs(root, G):
+    """Recreate the mini data set of loader_cases.npz as the files the loaders read."""
+    os.makedirs(root, exist_ok=True)
+    with open(os.path.join(root, "chrom.sizes"), "w") as f:
+        f.write("chr1\t248956422\nchr3\t%d\n" % int(G["chrom_size"]))
+    dirs = []
+    for s in range(int(G["n_species"])):
+        d = os.path.join(root, "hic_sp%d" % s)
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "chr3.%dK.txt" % (int(G["resolution"]) // 1000)), "w") as f:
+            for a, b, v in zip(G["sp%d_x1" % s], G["sp%d_x2" % s], G["sp%d_v" % s]):
+                f.write("%d\t%d\t%s\n" % (a, b, "NaN" if np.isnan(v) else repr(float(v))))
+        dirs.append(d)
+    np.savetxt(os.path.join(root, "chr3.synteny.txt"), G["synteny"], fmt="%d", delimiter="\t")
+    return dirs
+
+
+def make_loader_cases():
+    """utility.py:2507-2570, 2631-2662, 824-863 (multi_contact_matrix3A, output_multi_contactMtx,
+    mapping_Idx) and :2111-2189 (subregion1) on a mini chr3 (1 Mb bins, a synteny block across the
+    hg38 centromere).  Python-2 classic division in the alignment is patched to ``//``."""
+    import math
+    import tempfile
+    import pandas as pd
+    patches = [("math.ceil(chrom_size/resolution)", "math.ceil(chrom_size//resolution)"),
+               ("x1, x2 = x1/resolution, x2/resolution", "x1, x2 = x1//resolution, x2//resolution"),
+               # pandas >= 2 hands out read-only views; the reference writes -1 over NaN in place
+               ("np.asarray(data2[2])", "np.array(data2[2])")]
+    util = ref_loader.load_utility(["mapping_Idx", "output_multi_contactMtx", "multi_contact_matrix3A", "subregion1",
+                                    "multi_contact_matrix3A_single", "quantile_contact", "quantile_contact_vec"],
+                                   patches)
+    util.update({"pd": pd, "math": math, "os": os})
+    rng = np.random.default_rng(11)
+    res = 1000000
+    G = {"resolution": np.array(res), "chrom_size": np.array(198295559), "n_species": np.array(3),
+         "synteny": np.array([[60000000, 110000000, 50000000], [120000000, 140000000, 20000000]])}
+    ii, jj = np.triu_indices(80)
+    for s in range(3):
+        keep = rng.random(len(ii)) < (0.9, 0.6, 0.75)[s]
+        a, b = (ii[keep] + 60) * res, (jj[keep] + 60) * res
+        v = 100.0 / (1.0 + (jj[keep] - ii[keep])) * rng.gamma(2.0, 0.5, size=keep.sum())
+        v[rng.random(len(v)) < 0.02] = np.nan
+        G["sp%d_x1" % s], G["sp%d_x2" % s], G["sp%d_v" % s] = a, b, v
+    with tempfile.TemporaryDirectory() as root:
+        dirs = write_loader_inputs(root, G)
+        species = ["sp0", "sp1", "sp2"]
+        data = util["multi_contact_matrix3A"]("3", res, os.path.join(root, "chrom.sizes"), dirs, species, "", 0)
+        G["aligned_position"] = np.asarray(data.loc[:, [0, 1, 2]])
+        G["aligned_x"] = np.asarray(data.loc[:, species], dtype=np.float64)
+        G["quantiles"] = util["quantile_contact_vec"](["3"], res, os.path.join(root, "chrom.sizes"), dirs, species)
+        points = [np.array([90279522, 93797661])]
+        region_list, list1 = util["subregion1"](os.path.join(root, "chr3.synteny.txt"), 3, res, points, 0)
+        G["region_list"] = np.asarray([list(map(int, r)) for r in region_list])
+        G["list1"] = np.asarray([list(map(int, r)) for r in list1])
+        region_list, list1 = util["subregion1"](os.path.join(root, "chr3.synteny.txt"), 3, res, [], 0)
+        G["list1_nosplit"] = np.asarray([list(map(int, r)) for r in list1])
+    path = os.path.join(HERE, "loader_cases.npz")
+    np.savez_compressed(path, **G)
+    print("wrote", path, os.path.getsize(path), "bytes", G["aligned_x"].shape, G["list1"].shape)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not present")
     make_select_cases()
+    make_loader_cases()
     util = ref_loader.load_utility(["normalize_feature", "write_matrix_image_v1", "near_interpolation1",
                                     "near_interpolation1a", "write_matrix_array_v1"])
     util["THRESH1"] = 1e-05

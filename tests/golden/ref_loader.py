@@ -56,12 +56,18 @@ def _py3(src_lines, level):
     return textwrap.dedent(body)
 
 
-def load_functions(filename, names, level, namespace):
-    """Exec the named functions of ``filename`` (tab-indent ``level``) into ``namespace``."""
+def load_functions(filename, names, level, namespace, patches=()):
+    """Exec the named functions of ``filename`` (tab-indent ``level``) into ``namespace``.
+
+    ``patches``: (old, new) text replacements applied to the extracted source in memory -- only
+    for Python-2 semantics that Python 3 spells differently (classic integer division ``a/b`` on
+    integers -> ``a//b``); every caller lists its patches next to the call."""
     with open(os.path.join(REF, filename), encoding="utf-8", errors="replace") as f:
         lines = f.readlines()
     for n in names:
         code = _py3(_extract(lines, n, level), level)
+        for old, new in patches:
+            code = code.replace(old, new)
         exec(compile(code, "%s:%s" % (filename, n), "exec"), namespace)
     return namespace
 
@@ -90,8 +96,8 @@ def build_reference_class(extra_globals):
     return cls
 
 
-def load_utility(names):
+def load_utility(names, patches=()):
     import numpy as np
     g = {"np": np}
-    load_functions("utility.py", names, 0, g)
+    load_functions("utility.py", names, 0, g, patches)
     return g

@@ -158,3 +158,44 @@ def test_region_loader_end_to_end(util):
     assert rid == 0 and lenvec == [ref[0].shape[0], n1, n1, position[idx].min(), position[idx].min(), 5, 1, 21]
     from phylo_hmrf_b200 import utility
     assert edges.shape == (utility._lib.lib().phmrf_grid_edge_count(1, n1, n1, 8), 3)
+
+
+def test_chromosome_loader_end_to_end(util, tmp_path):
+    """loader.load_data_chromosome2 on the mini chr3 data set of tests/golden/loader_cases.npz (aligned by
+    the reference itself): alignment -> rescale + log -> regions (one synteny block split at the
+    centromere: two diagonal parts and their off-diagonal pair; one plain block) -> image pipeline on the
+    GPU, against the oracle composition."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_prep import write_loader_inputs
+    from phylo_hmrf_b200 import loader
+    L = np.load(os.path.join(os.path.dirname(__file__), "golden", "loader_cases.npz"))
+    dirs = write_loader_inputs(str(tmp_path), L)
+    res = int(L["resolution"])
+    species = ["sp0", "sp1", "sp2"]
+    samples, len_vec, edges = loader.load_data_chromosome2([3], 60.0, 0, res, 8, 0, 0.0, 0, str(tmp_path / "chrom.sizes"),
+                                                           dirs, species, str(tmp_path))
+    x, _, _, _ = po.normalize_feature(L["aligned_x"], 0, 60.0)
+    x = po.log_transform(x)
+    position = L["aligned_position"]
+    ref_blocks = []
+    for row in L["list1"]:
+        xs, idx = util.select_valuesPosition1_2(position, x, "", row[0], row[1], row[2], row[3], res, 0)
+        p = position[idx, :2]
+        if row[0] == row[2] and row[1] == row[3]:
+            ref_blocks.append(po.image_pipeline_diag(xs, p, filter_mode=0, niter=5, kappa=50, gamma=0.1)[0])
+        else:
+            s1, s2 = p[:, 0].min(), p[:, 1].min()
+            n1, n2 = p[:, 0].max() - s1 + 1, p[:, 1].max() - s2 + 1
+            mtx = np.zeros((n1, n2, xs.shape[1]))
+            mtx[p[:, 0] - s1, p[:, 1] - s2] = xs
+            for c in range(xs.shape[1]):
+                plane = po.near_interpolation1a(mtx[:, :, c].copy())
+                mtx[:, :, c] = po.anisotropic_diffusion(plane, 5, 50, 0.1)
+            ref_blocks.append(mtx.reshape(n1 * n2, -1))
+    ref = np.concatenate(ref_blocks, axis=0)
+    assert samples.shape == ref.shape
+    np.testing.assert_allclose(samples, ref, rtol=2e-5, atol=2e-6)
+    assert [lv[8] for lv in len_vec] == [1, 0, 1, 1] and len_vec[-1][2] == len(samples) and len(edges) == 4
+    for lv, blk in zip(len_vec, ref_blocks):
+        assert lv[0] == len(blk) and lv[2] - lv[1] == len(blk)
