@@ -99,46 +99,30 @@ def quantile_contact_vec(chrom_vec, resolution, ref_filename, filename_list, spe
 
 
 def subregion1(filename, chrom_id, resolution, region_points, type_id):
-    """utility.py:2111-2189: synteny blocks (start, stop, length per line) -> (region_list, list1); a
-    block that spans a listed centromere is split, and every pair of its parts becomes a region.
-    list1 rows: [position1, position2, position1a, position2a, length, length_a, region_id, region_id1,
-    chrom_id]."""
-    t_lenvec = np.loadtxt(filename, dtype='int', delimiter='\t')
-    region_list = []
-    if t_lenvec.ndim > 1:
-        for i in range(t_lenvec.shape[0]):
-            region_list.append(np.hstack((t_lenvec[i, 0:3], i)))
-    else:
-        region_list.append(np.hstack((t_lenvec[0:3], 0)))
-    threshold = resolution * 2
-    for k in range(len(region_points)):
-        vec1 = np.asarray(region_list)
-        point1, point2 = region_points[k][0], region_points[k][1]
-        b = np.where((vec1[:, 0] < point1 - threshold) & (vec1[:, 1] > point2 + threshold))[0]
-        if len(b) > 0:
-            id1 = b[0]
-            region_id = vec1[id1, 3]
-            start1, stop1 = vec1[id1, 0], point1
-            start2, stop2 = point2, vec1[id1, 1]
-            region_list[id1] = [start2, stop2, stop2 - start2, region_id]
-            region_list.insert(id1, [start1, stop1, stop1 - start1, region_id])
-    region_list1 = np.asarray(region_list)
-    region_idvec1 = region_list1[:, -1]
-    list1 = []
-    region_id1 = 0
-    for region_id in np.sort(np.unique(region_idvec1)):
-        b = np.where(region_idvec1 == region_id)[0]
-        if len(b) == 1:
-            p1, p2, length = region_list[b[0]][0], region_list[b[0]][1], region_list[b[0]][2]
-            list1.append([p1, p2, p1, p2, length, length, region_id, region_id1, chrom_id])
-            region_id1 += 1
-        else:
-            for i in range(len(b)):
-                for j in range(i, len(b)):
-                    t1, t2 = region_list[b[i]], region_list[b[j]]
-                    list1.append([t1[0], t1[1], t2[0], t2[1], t1[2], t2[2], region_id, region_id1, chrom_id])
-                    region_id1 += 1
-    return region_list, list1
+    """utility.py:2111-2189: synteny blocks (start, stop, length per line) -> (blocks, regions).  A block
+    that spans a listed centromere (by more than two bins either side) is cut into the part before and the
+    part after it, both keeping the block's id; every block id then yields its diagonal region, or -- when
+    it was cut -- every ordered pair (i <= j) of its parts.  A region row is
+    [start, stop, start_a, stop_a, length, length_a, block id, running region number, chrom_id]."""
+    table = np.atleast_2d(np.loadtxt(filename, dtype='int', delimiter='\t'))
+    blocks = [[int(r[0]), int(r[1]), int(r[2]), k] for k, r in enumerate(table)]
+    margin = 2 * resolution
+    for centro_start, centro_stop in ((p[0], p[1]) for p in region_points):
+        hit = next((k for k, b in enumerate(blocks) if b[0] < centro_start - margin and b[1] > centro_stop + margin),
+                   None)
+        if hit is None:
+            continue
+        start, stop, _, block_id = blocks[hit]
+        blocks[hit:hit + 1] = [[start, centro_start, centro_start - start, block_id],
+                               [centro_stop, stop, stop - centro_stop, block_id]]
+    regions = []
+    for block_id in sorted({b[3] for b in blocks}):
+        parts = [b for b in blocks if b[3] == block_id]
+        for i, first in enumerate(parts):
+            for second in parts[i:]:
+                regions.append([first[0], first[1], second[0], second[1], first[2], second[2], block_id,
+                                len(regions), chrom_id])
+    return blocks, regions
 
 
 # centromere positions of chr3 and chr6 in hg38 (utility.py:383)

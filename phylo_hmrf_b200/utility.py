@@ -145,28 +145,26 @@ def write_matrix_image_Ctrl_sym1(value, pos, output_filename1, output_filename2,
 def select_valuesPosition1_2(position, x, output_filename, position1, position2, position1a, position2a, resolution,
                              border_type=0):
     """utility.py:1331-1364: rows of the aligned matrix whose bin pair lies in the region
-    [position1, position2] x [position1a, position2a] (genomic coordinates).  Host NumPy."""
+    [position1, position2] x [position1a, position2a] (genomic coordinates; a bin pair is placed at the
+    start of its first bin and, for border types 0 and 1, the END of its second bin).  Host NumPy.
+    Returns (x[rows], rows)."""
     position = np.asarray(position)
+    first = position[:, 0] * resolution
     if border_type == 0:
-        x1, x2 = position[:, 0] * resolution, (position[:, 1] + 1) * resolution
-        b = (x1 >= position1) & (x1 <= position2) & (x2 >= position1a) & (x2 <= position2a)
+        second = (position[:, 1] + 1) * resolution
+        inside = (first >= position1) & (first <= position2) & (second >= position1a) & (second <= position2a)
     elif border_type == 1:
-        x1, x2 = position[:, 0] * resolution, (position[:, 1] + 1) * resolution
-        b = (x1 >= position1) & (x2 <= position2)
+        inside = (first >= position1) & ((position[:, 1] + 1) * resolution <= position2)
     else:
-        x1, x2 = position[:, 0] * resolution, position[:, 1] * resolution
-        b = (x1 >= position1) & (x1 < position2) & (x2 >= position1a) & (x2 < position2a)
-    b1 = np.where(b)[0]
-    if output_filename != "":
+        second = position[:, 1] * resolution
+        inside = (first >= position1) & (first < position2) & (second >= position1a) & (second < position2a)
+    rows = np.flatnonzero(inside)
+    if output_filename != "":   # the reference's tab-separated dump: three position columns, then the species
         import pandas as pd
-        n_fields = 3 + x.shape[1]
-        data2 = pd.DataFrame(columns=range(n_fields))
-        for i in range(3):
-            data2[i] = position[b1, i]
-        for i in range(3, n_fields):
-            data2[i] = x[b1, i - 3]
-        data2.to_csv(output_filename, index=False, sep='\t')
-    return x[b1, :], b1
+        table = pd.DataFrame(np.hstack([position[rows, :3], np.asarray(x)[rows]]))
+        table[[0, 1, 2]] = position[rows, :3]
+        table.to_csv(output_filename, index=False, sep='\t')
+    return x[rows, :], rows
 
 
 def load_data_chromosome_sub3(region_id, chrom_id, region_list, x, position, param_vec, m_queue, device=0):
