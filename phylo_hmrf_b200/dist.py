@@ -60,3 +60,54 @@ def global_dwf(absmax_local, wmax_local, vmax, dist):
     t = torch.tensor([absmax_local, wmax_local], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return max(float(t[0]), float(t[1]) * vmax) + 1e-10
+
+
+def region_row_sizes(kind, n1, n2):
+    """Nodes per image row of a region: kind 1 = diagonal (upper triangle of an n1-bin window: row r holds
+    n1 - r nodes), kind 0 = off-diagonal n1 x n2 block."""
+    if kind == 1:
+        return np.arange(int(n1), 0, -1, dtype=np.int64)
+    return np.full(int(n1), int(n2), dtype=np.int64)
+
+
+def split_rows(row_sizes, n_bands):
+    """Contiguous row ranges [r0, r1) balancing the NODE count (not the row count) across bands."""
+    row_sizes = np.asarray(row_sizes, dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(row_sizes)])
+    total, n_rows = int(starts[-1]), len(row_sizes)
+    n_bands = max(1, min(int(n_bands), n_rows))
+    cuts = [0]
+    for b in range(1, n_bands):
+        c = int(np.searchsorted(starts, total * b / n_bands))
+        cuts.append(min(max(c, cuts[-1] + 1), n_rows - (n_bands - b)))   # every band keeps at least one row
+    cuts.append(n_rows)
+    return [(cuts[i], cuts[i + 1]) for i in range(n_bands)]
+
+
+def plan_shards(regions, world_size):
+    """Assign the regions of one EM iteration to ``world_size`` GPUs: regions are the
+    reference's own unit of parallelism (one forked process each, base.py:357-362); a region holding more
+    than 1/world_size of all nodes is cut into row bands of about that size (balanced by node count), and
+    the pieces go to the least-loaded rank, largest first.
+
+    regions: sequence of (kind, n1, n2) -- the entries 6, 1, 2 of a ``len_vec`` row.
+    Returns ``plan[rank] = [(region_id, row0, row1, n_nodes), ...]`` (deterministic, identical on every rank)."""
+    world_size = int(world_size)
+    sizes = [region_row_sizes(*r) for r in regions]
+    totals = [int(s.sum()) for s in sizes]
+    cap = max(1.0, sum(totals) / float(world_size))
+    pieces = []
+    for rid, (rows, n) in enumerate(zip(sizes, totals)):
+        n_bands = int(np.ceil(n / cap)) if n > cap else 1
+        starts = np.concatenate([[0], np.cumsum(rows)])
+        for r0, r1 in split_rows(rows, n_bands):
+            pieces.append((rid, r0, r1, int(starts[r1] - starts[r0])))
+    load = [0] * world_size
+    plan = [[] for _ in range(world_size)]
+    for piece in sorted(pieces, key=lambda p: (-p[3], p[0], p[1])):
+        rank = min(range(world_size), key=lambda r: (load[r], r))
+        plan[rank].append(piece)
+        load[rank] += piece[3]
+    for p in plan:
+        p.sort(key=lambda q: (q[0], q[1]))
+    return plan

@@ -92,3 +92,35 @@ def test_two_rank_band_sharding_matches_single_region(tmp_path):
     assert int(got["n_total"]) == whole["n_own"]
     np.testing.assert_allclose(got["stats"], flat, rtol=1e-12)
     np.testing.assert_allclose(got["costs"], ref[1:], rtol=1e-12)
+
+
+def test_plan_shards_covers_every_row_once_and_balances():
+    from phylo_hmrf_b200 import dist as pdist
+    # BASELINE config 4: chr1..22 at 50 kb, one diagonal region per chromosome (bins from hg38.chrom.sizes)
+    sizes = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+             133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+             58617616, 64444167, 46709983, 50818468]
+    regions = [(1, s // 50000, s // 50000) for s in sizes]
+    regions.append((0, 120, 340))          # and one off-diagonal block
+    for world in (1, 2, 3, 8):
+        plan = pdist.plan_shards(regions, world)
+        assert len(plan) == world and plan == pdist.plan_shards(regions, world)
+        seen = {}
+        for rank, pieces in enumerate(plan):
+            for rid, r0, r1, n in pieces:
+                rows = pdist.region_row_sizes(*regions[rid])
+                assert 0 <= r0 < r1 <= len(rows) and n == int(rows[r0:r1].sum())
+                seen.setdefault(rid, []).append((r0, r1))
+        for rid, reg in enumerate(regions):
+            spans = sorted(seen[rid])
+            assert spans[0][0] == 0 and spans[-1][1] == reg[1]
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        loads = [sum(p[3] for p in pieces) for pieces in plan]
+        total = sum(int(pdist.region_row_sizes(*r).sum()) for r in regions)
+        assert sum(loads) == total == 89321427 + 120 * 340
+        assert max(loads) <= 1.06 * total / world
+    # one big region on 8 GPUs: eight bands of (almost) equal node count, like bench.py's workload
+    plan = pdist.plan_shards([(1, 24895, 24895)], 8)
+    loads = [sum(p[3] for p in pieces) for pieces in plan]
+    assert sorted(p[0][1:3] for p in plan)[0][0] == 0 and max(loads) - min(loads) < 2 * 24895
+    assert pdist.split_rows([5, 1, 1], 3) == [(0, 1), (1, 2), (2, 3)]
