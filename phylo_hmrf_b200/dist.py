@@ -111,3 +111,34 @@ def plan_shards(regions, world_size):
     for p in plan:
         p.sort(key=lambda q: (q[0], q[1]))
     return plan
+
+
+def assign_regions(region_sizes, world_size):
+    """Whole regions to ranks, largest first onto the least-loaded rank (the graph cut needs a region in
+    one place).  Returns ``owner[region_id] = rank`` (deterministic, identical on every rank)."""
+    load = [0] * int(world_size)
+    owner = [0] * len(region_sizes)
+    for rid in sorted(range(len(region_sizes)), key=lambda r: (-int(region_sizes[r]), r)):
+        rank = min(range(len(load)), key=lambda q: (load[q], q))
+        owner[rid] = rank
+        load[rank] += int(region_sizes[rid])
+    return owner
+
+
+def world_info():
+    """(world_size, rank) of the initialised torch.distributed process group, else (1, 0)."""
+    try:
+        import torch.distributed as td
+    except ImportError:
+        return 1, 0
+    if td.is_available() and td.is_initialized():
+        return td.get_world_size(), td.get_rank()
+    return 1, 0
+
+
+def all_gather_results(results):
+    """The per-region result tuples of every rank (the reference's queue, base.py:372), on every rank."""
+    import torch.distributed as td
+    parts = [None] * td.get_world_size()
+    td.all_gather_object(parts, results)
+    return [item for part in parts for item in part]

@@ -336,18 +336,29 @@ class phyloHMRF(object):
         params_vecList = []
         t_labels = np.zeros(n_samples)
         workers = n_threads or min(num_region, 8)
+        # one process per GPU (torchrun): whole regions are dealt to the ranks by node count, every rank
+        # gathers all result tuples and then runs the same (deterministic) aggregation and M-step
+        from . import dist as _pdist
+        world, rank = _pdist.world_info()
+        if world > 1:
+            owner = _pdist.assign_regions([lv[0] for lv in len_vec], world)
+            my_regions = [r for r in range(num_region) if owner[r] == rank]
+        else:
+            my_regions = list(range(num_region))
 
         for iter in range(max_iter):
             stats = self._initialize_sufficient_statistics()
             self._sync_model()
             self.queue = _queue.Queue()
-            if workers > 1 and num_region > 1:
+            if workers > 1 and len(my_regions) > 1:
                 with ThreadPoolExecutor(max_workers=workers) as pool:
-                    list(pool.map(lambda r: self._predict_posteriors(X, len_vec, r, self.queue), range(num_region)))
+                    list(pool.map(lambda r: self._predict_posteriors(X, len_vec, r, self.queue), my_regions))
             else:
-                for region_id in range(0, num_region):
+                for region_id in my_regions:
                     self._predict_posteriors(X, len_vec, region_id, self.queue)
-            results = [self.queue.get() for _ in range(num_region)]
+            results = [self.queue.get() for _ in range(len(my_regions))]
+            if world > 1:
+                results = _pdist.all_gather_results(results)
 
             pairwise_cost1, pairwise_cost, unary_cost, cost1 = 0, 0, 0, 0
             id1 = 3

@@ -124,3 +124,65 @@ def test_plan_shards_covers_every_row_once_and_balances():
     loads = [sum(p[3] for p in pieces) for pieces in plan]
     assert sorted(p[0][1:3] for p in plan)[0][0] == 0 and max(loads) - min(loads) < 2 * 24895
     assert pdist.split_rows([5, 1, 1], 3) == [(0, 1), (1, 2), (2, 3)]
+
+
+def _em_worker(rank, world, port, out_dir):
+    """Two ranks run the re-hosted EM driver on the scripted model: each executes only the regions it owns,
+    the result tuples are all-gathered, and every rank must end with the reference driver's outcome."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import fit_script as fs
+    from phylo_hmrf_b200.hmrf import phyloHMRF
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        owner = pdist.assign_regions([lv[0] for lv in fs.LEN_VEC], world)
+        n_mine = sum(1 for o in owner if o == rank)
+
+        class Driver(fs.ScriptedModel, phyloHMRF):
+            def _predict_posteriors(self, X, len_vec, region_id, m_queue):
+                assert owner[region_id] == rank          # a rank only ever works on its own regions
+                it = self.iteration
+                fs.ScriptedModel._predict_posteriors(self, X, len_vec, region_id, m_queue)
+                # the script advances its clock after len(len_vec) calls; here a rank makes n_mine per iteration
+                self.iteration, self.calls_this_iter = it, (self.calls_this_iter % len(len_vec))
+                self._mine = getattr(self, "_mine", 0) + 1
+                if self._mine == n_mine:
+                    self._mine, self.calls_this_iter, self.iteration = 0, 0, it + 1
+                return True
+
+        name = "converges"
+        m_iter, thr, _ = fs.SCENARIOS[name]
+        m = object.__new__(Driver)
+        m.script(name)
+        res = m.fit_accumulate_test(np.zeros((fs.N, fs.D)), fs.LEN_VEC, thr, "test", m_iter, n_threads=1)
+        np.savez(os.path.join(out_dir, "em_rank%d.npz" % rank), cost_vec=res[5], params_vec=res[0], t_labels=res[6],
+                 it=np.array([res[3], res[4]]), n_iter=m.iteration, owner=np.array(owner))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_em_driver_matches_the_reference_driver(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_em_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_driver.npz"))
+    for rank in (0, 1):
+        got = np.load(str(tmp_path / ("em_rank%d.npz" % rank)))
+        assert sorted(got["owner"].tolist()) == [0, 1]
+        assert int(got["n_iter"]) == int(gold["converges_n_iter"])
+        np.testing.assert_array_equal(got["cost_vec"], gold["converges_cost_vec"])
+        np.testing.assert_array_equal(got["params_vec"], gold["converges_params_vec"])
+        np.testing.assert_array_equal(got["t_labels"], gold["converges_t_labels"])
+        assert got["it"].tolist() == gold["converges_it"].tolist()
+
+
+def test_assign_regions_is_balanced_and_deterministic():
+    sizes = [100, 90, 50, 40, 30, 20, 10, 5]
+    owner = pdist.assign_regions(sizes, 3)
+    assert owner == pdist.assign_regions(sizes, 3) and set(owner) == {0, 1, 2}
+    loads = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(3)]
+    assert max(loads) - min(loads) <= 20
+    assert pdist.assign_regions([7, 7], 1) == [0, 0]
