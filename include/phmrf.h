@@ -57,6 +57,17 @@ int phmrf_ctx_destroy(phmrf_ctx *ctx);
  * produced by _pairwise_potential takes the fast path, any other V the general one. */
 int phmrf_set_model(phmrf_ctx *ctx, const double *means, const double *covars, const double *V);
 
+/* The three scale factors of pygco's float -> int conversion (yujiali/pygco pygco.py, behind
+ * phylo_hmrf.py:496-498): _UNARY_FLOAT_PRECISION = 1e5 for the unary costs,
+ * _PAIRWISE_FLOAT_PRECISION = 1e3 for the edge weights and _SMOOTH_COST_PRECISION = 1e2 for the
+ * label compatibility matrix V (pygco's own rule: "pairwise * smooth = unary", 1e3 * 1e2 = 1e5,
+ * so that w_ij * V[a,b] lands on the unary's scale).  These are the defaults; the setter exists
+ * because pygco is not vendored by the reference and is unpinned (README.md:84), so a maintainer
+ * can match whatever their installed pygco uses (INTEGRATION.md shows how to check). */
+int phmrf_set_quantiser(phmrf_ctx *ctx, double unary_precision, double pairwise_precision, double smooth_precision);
+int phmrf_get_quantiser(const phmrf_ctx *ctx, double *unary_precision, double *pairwise_precision,
+                        double *smooth_precision);
+
 /* ------------------------------------------------------------------ region ------------ */
 
 /* Replaces the per-region inputs of _predict_posteriors (phylo_hmrf.py:297-322): X[s1:s2]
@@ -101,7 +112,8 @@ int phmrf_set_logprob(phmrf_region *r, const double *logprob);
 /* The float->int conversion inside pygco.cut_general_graph (yujiali/pygco, called at
  * phylo_hmrf.py:496-498 with down_weight_factor=None):
  *   dwf = max(max|unary|, max|w|*max(V)) + 1e-10
- *   unary_i32 = trunc((-logp/dwf)*1e5); w_i32 = trunc((w/dwf)*1e3); V_i32 = trunc(V*1e3)
+ *   unary_i32 = trunc((-logp/dwf)*1e5); w_i32 = trunc((w/dwf)*1e3); V_i32 = trunc(V*1e2)
+ * (scale factors: phmrf_set_quantiser)
  * dwf_in > 0 overrides the region-local value (bands of one region must share the
  * all-reduced maximum).  Any output pointer may be NULL (the integer unary then stays on
  * the device for phmrf_labels_argmin_unary).  Entries whose scaled value lies within

@@ -40,7 +40,8 @@ SMALL_EPS = 1e-16  # phylo_hmrf.py:49
 
 # --- pygco (yujiali/pygco, pygco.py) constants: third-party, not vendored ---------
 PYGCO_UNARY_FLOAT_PRECISION = 100000  # _UNARY_FLOAT_PRECISION
-PYGCO_PAIRWISE_FLOAT_PRECISION = 1000  # _PAIRWISE_FLOAT_PRECISION
+PYGCO_PAIRWISE_FLOAT_PRECISION = 1000  # _PAIRWISE_FLOAT_PRECISION (edge weights)
+PYGCO_SMOOTH_COST_PRECISION = 100  # _SMOOTH_COST_PRECISION (label compatibility V): "pairwise * smooth = unary"
 PYGCO_SMALL_CONSTANT = 1e-10  # _SMALL_CONSTANT
 
 
@@ -120,7 +121,8 @@ def pygco_down_weight_factor(unary, edge_weights, V):
     return max(np.abs(unary).max(), np.abs(edge_weights).max() * V.max()) + PYGCO_SMALL_CONSTANT
 
 
-def pygco_quantise(unary, edge_weights, V, down_weight_factor=None):
+def pygco_quantise(unary, edge_weights, V, down_weight_factor=None, unary_precision=PYGCO_UNARY_FLOAT_PRECISION,
+                   pairwise_precision=PYGCO_PAIRWISE_FLOAT_PRECISION, smooth_precision=PYGCO_SMOOTH_COST_PRECISION):
     """The three integer arrays pygco hands to GCO: divide by dwf, multiply by the
     precision constant, ``astype(np.intc)`` (C cast: truncation toward zero).
     Returns (unary_i32[N,K], w_i32[E], V_i32[K,K], dwf)."""
@@ -128,9 +130,9 @@ def pygco_quantise(unary, edge_weights, V, down_weight_factor=None):
     edge_weights = np.asarray(edge_weights, dtype=np.float64)
     V = np.asarray(V, dtype=np.float64)
     dwf = pygco_down_weight_factor(unary, edge_weights, V) if down_weight_factor is None else down_weight_factor
-    u_i = ((unary / dwf) * PYGCO_UNARY_FLOAT_PRECISION).astype(np.intc)
-    w_i = ((edge_weights / dwf) * PYGCO_PAIRWISE_FLOAT_PRECISION).astype(np.intc)
-    V_i = (V * PYGCO_PAIRWISE_FLOAT_PRECISION).astype(np.intc)
+    u_i = ((unary / dwf) * unary_precision).astype(np.intc)
+    w_i = ((edge_weights / dwf) * pairwise_precision).astype(np.intc)
+    V_i = (V * smooth_precision).astype(np.intc)
     return u_i, w_i, V_i, dwf
 
 

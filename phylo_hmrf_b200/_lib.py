@@ -36,6 +36,8 @@ SIGNATURES = {
     "phmrf_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "phmrf_ctx_destroy": (C.c_int, [_vp]),
     "phmrf_set_model": (C.c_int, [_vp, _c_double_p, _c_double_p, _c_double_p]),
+    "phmrf_set_quantiser": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
+    "phmrf_get_quantiser": (C.c_int, [_vp, _c_double_p, _c_double_p, _c_double_p]),
     "phmrf_region_create": (C.c_int, [_vp, _c_double_p, C.c_int64, C.c_int64, C.c_int64, _c_int64_p, _c_double_p,
                                       C.c_int64, _vp, C.POINTER(_vp)]),
     "phmrf_region_update_X": (C.c_int, [_vp, _c_double_p]),

@@ -33,6 +33,8 @@ struct phmrf_ctx {
     bool has_model = false;
     bool potts = false;
     double beta = 0.0, vmax = 0.0;
+    // pygco's float -> int scale factors (phmrf_set_quantiser): unary, edge weights, V
+    double uprec = 100000.0, wprec = 1000.0, sprec = 100.0;
     unsigned long long version = 0;
     std::vector<double> packed;  // K * model_stride(D)
     std::vector<double> V;       // K*K
@@ -48,7 +50,8 @@ struct phmrf_region {
     int W = 0;
     double wmax = 0.0;
     double *d_X = nullptr;       // [D][ld]
-    double *d_logp = nullptr;    // [K][ld]
+    double *d_logp = nullptr;    // tiled [ld/32][KP][32] (common.cuh lp_index)
+    double *d_rowmax = nullptr;  // [ld] max_k logp per node (written by the quantise kernel)
     int32_t *d_unary = nullptr;  // [n][K]
     int32_t *d_labels = nullptr; // [n_window]
     int32_t *d_nbr_id = nullptr; // [W][ld]
@@ -66,9 +69,10 @@ struct phmrf_region {
     double *d_partials = nullptr;
     double *d_stats = nullptr;
     int *d_flags = nullptr;
+    long long *d_badlabel = nullptr;  // [1] first out-of-range label index, -1 if none
     double *d_scratch = nullptr;  // [K][ld] posteriors / AoS staging, allocated on demand
     int64_t scratch_elems = 0;
-    bool have_logp = false, have_unary = false, have_labels = false;
+    bool have_logp = false, have_unary = false, have_labels = false, have_rowmax = false;
     int64_t bytes = 0;
 };
 
@@ -240,6 +244,29 @@ int phmrf_set_model(phmrf_ctx *ctx, const double *means, const double *covars, c
     return PHMRF_OK;
 }
 
+int phmrf_set_quantiser(phmrf_ctx *ctx, double unary_precision, double pairwise_precision, double smooth_precision) {
+    // |scaled value| must stay below 2^31 for the int32 conversion; pygco's own limit is GCO's 1e7 per term
+    if (!ctx || !(unary_precision >= 1.0 && unary_precision <= 1e9) ||
+        !(pairwise_precision >= 1.0 && pairwise_precision <= 1e9) ||
+        !(smooth_precision >= 1.0 && smooth_precision <= 1e9)) {
+        set_error("phmrf_set_quantiser: precisions must lie in [1, 1e9]");
+        return PHMRF_E_INVALID;
+    }
+    ctx->uprec = unary_precision;
+    ctx->wprec = pairwise_precision;
+    ctx->sprec = smooth_precision;
+    return PHMRF_OK;
+}
+
+int phmrf_get_quantiser(const phmrf_ctx *ctx, double *unary_precision, double *pairwise_precision,
+                        double *smooth_precision) {
+    if (!ctx) return PHMRF_E_INVALID;
+    if (unary_precision) *unary_precision = ctx->uprec;
+    if (pairwise_precision) *pairwise_precision = ctx->wprec;
+    if (smooth_precision) *smooth_precision = ctx->sprec;
+    return PHMRF_OK;
+}
+
 int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t n_window, int64_t own_offset,
                         const int64_t *edge_ids, const double *edge_w, int64_t n_edges, void *stream,
                         phmrf_region **out) {
@@ -296,6 +323,7 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
     }
     TRY(dev_alloc(r, &r->d_X, (int64_t)D * ld));
     TRY(dev_alloc(r, &r->d_logp, (int64_t)logp_rows(K) * ld));
+    TRY(dev_alloc(r, &r->d_rowmax, ld));
     TRY(dev_alloc(r, &r->d_unary, n_own * K));
     TRY(dev_alloc(r, &r->d_labels, n_window));
     TRY(dev_alloc(r, &r->d_nbr_id, (int64_t)W * ld));
@@ -309,13 +337,14 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
     TRY(dev_alloc(r, &r->d_partials, (int64_t)ctx->sm_count * ((int64_t)K * F + 3)));
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
     TRY(dev_alloc(r, &r->d_flags, 1));
+    TRY(dev_alloc(r, &r->d_badlabel, 1));
 
     // X: upload row-major, transpose on the device into the feature-major layout
     if (n_own > 0) {
         TRY(ensure_scratch(r, n_own * D));
         if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
-            cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess ||
-            launch_fill(r->d_logp + (int64_t)K * ld, kLogpPad, (int64_t)(logp_rows(K) - K) * ld, r->stream) != PHMRF_OK ||
+            cudaMemsetAsync(r->d_rowmax, 0, sizeof(double) * ld, r->stream) != cudaSuccess ||
+            launch_logp_init(r->d_logp, ld, K, r->stream) != PHMRF_OK ||
             cudaMemcpyAsync(r->d_scratch, X, sizeof(double) * n_own * D, cudaMemcpyHostToDevice, r->stream) !=
                 cudaSuccess) {
             cudaError_t err = cudaGetLastError();
@@ -425,6 +454,7 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
     r->E = n_edges;
     TRY(dev_alloc(r, &r->d_X, (int64_t)D * ld));
     TRY(dev_alloc(r, &r->d_logp, (int64_t)logp_rows(K) * ld));
+    TRY(dev_alloc(r, &r->d_rowmax, ld));
     TRY(dev_alloc(r, &r->d_unary, n_own * K));
     TRY(dev_alloc(r, &r->d_labels, n_window));
     TRY(dev_alloc(r, &r->d_nbr_id, (int64_t)r->W * ld));
@@ -438,9 +468,10 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
     TRY(dev_alloc(r, &r->d_partials, (int64_t)ctx->sm_count * ((int64_t)K * F + 3)));
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
     TRY(dev_alloc(r, &r->d_flags, 1));
+    TRY(dev_alloc(r, &r->d_badlabel, 1));
     if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
-        cudaMemsetAsync(r->d_logp, 0, sizeof(double) * K * ld, r->stream) != cudaSuccess ||
-        launch_fill(r->d_logp + (int64_t)K * ld, kLogpPad, (int64_t)(logp_rows(K) - K) * ld, r->stream) != PHMRF_OK) {
+        cudaMemsetAsync(r->d_rowmax, 0, sizeof(double) * ld, r->stream) != cudaSuccess ||
+        launch_logp_init(r->d_logp, ld, K, r->stream) != PHMRF_OK) {
         cudaError_t err = cudaGetLastError();
         cudaFree(dXw);
         phmrf_region_destroy(r);
@@ -505,6 +536,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     if (r->stream) cudaStreamSynchronize(r->stream);
     cudaFree(r->d_X);
     cudaFree(r->d_logp);
+    cudaFree(r->d_rowmax);
     cudaFree(r->d_unary);
     cudaFree(r->d_labels);
     cudaFree(r->d_nbr_id);
@@ -519,6 +551,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     cudaFree(r->d_partials);
     cudaFree(r->d_stats);
     cudaFree(r->d_flags);
+    cudaFree(r->d_badlabel);
     cudaFree(r->d_scratch);
     if (r->own_stream) cudaStreamDestroy(r->stream);
     cudaGetLastError();
@@ -562,6 +595,7 @@ int phmrf_emit_loglik_async(phmrf_region *r) {
     if (rc == PHMRF_OK) {
         r->have_logp = true;
         r->have_unary = false;
+        r->have_rowmax = false;
     }
     return rc;
 }
@@ -589,7 +623,7 @@ int phmrf_get_logprob(phmrf_region *r, double *logprob_out) {
     if (r->n == 0) return PHMRF_OK;
     const int K = r->ctx->K;
     if ((rc = ensure_scratch(r, r->n * K)) != PHMRF_OK) return rc;
-    if ((rc = launch_soa_to_aos(r->d_logp, r->d_scratch, r->n, K, r->ld, r->stream)) != PHMRF_OK) return rc;
+    if ((rc = launch_logp_to_aos(r->d_logp, r->d_scratch, r->n, K, r->stream)) != PHMRF_OK) return rc;
     PHMRF_CUDA(cudaMemcpyAsync(logprob_out, r->d_scratch, sizeof(double) * r->n * K, cudaMemcpyDeviceToHost,
                                r->stream));
     PHMRF_CUDA(cudaStreamSynchronize(r->stream));
@@ -606,10 +640,14 @@ int phmrf_quantise_async(phmrf_region *r, double dwf_in, double tol) {
     int rc = set_device(ctx);
     if (rc) return rc;
     if ((rc = launch_dwf(r->d_absmax, r->wmax, ctx->vmax, dwf_in, r->d_dwf, r->stream)) != PHMRF_OK) return rc;
-    if ((rc = launch_quantise_unary(r->d_logp, r->n, r->ld, ctx->K, r->d_dwf, tol, r->d_unary, r->d_blist, r->bcap,
-                                    r->d_absmax + 1, ctx->sm_count, r->stream)) != PHMRF_OK)
+    // one launch: integer unary + per-node max + integer edge weights (pygco converts the edge
+    // weights on every call, the down-weight factor changes with the model)
+    if ((rc = launch_quantise(r->d_logp, r->n, ctx->K, r->d_dwf, tol, ctx->uprec, r->d_unary, r->d_rowmax, r->d_blist,
+                              r->bcap, r->d_absmax + 1, r->E > 0 ? r->d_edge_w : nullptr, r->E, ctx->wprec,
+                              r->d_edge_wi, ctx->sm_count, r->stream)) != PHMRF_OK)
         return rc;
     r->have_unary = true;
+    r->have_rowmax = true;
     return PHMRF_OK;
 }
 
@@ -620,10 +658,8 @@ int phmrf_quantise(phmrf_region *r, double dwf_in, double tol, int32_t *unary_i3
     if (rc) return rc;
     phmrf_ctx *ctx = r->ctx;
     const int K = ctx->K;
-    if (w_i32_out && r->E > 0) {
-        if ((rc = launch_quantise_edges(r->d_edge_w, r->E, r->d_dwf, r->d_edge_wi, r->stream)) != PHMRF_OK) return rc;
+    if (w_i32_out && r->E > 0)
         PHMRF_CUDA(cudaMemcpyAsync(w_i32_out, r->d_edge_wi, sizeof(int32_t) * r->E, cudaMemcpyDeviceToHost, r->stream));
-    }
     if (unary_i32_out && r->n > 0)
         PHMRF_CUDA(cudaMemcpyAsync(unary_i32_out, r->d_unary, sizeof(int32_t) * r->n * K, cudaMemcpyDeviceToHost,
                                    r->stream));
@@ -639,25 +675,28 @@ int phmrf_quantise(phmrf_region *r, double dwf_in, double tol, int32_t *unary_i3
         if (m > r->bcap) m = r->bcap;
         PHMRF_CUDA(cudaMemcpy(boundary_idx, r->d_blist, sizeof(long long) * m, cudaMemcpyDeviceToHost));
     }
-    if (V_i32_out)  // K*K values: host (numpy: (V * 1000).astype(intc))
-        for (int i = 0; i < K * K; ++i) V_i32_out[i] = (int32_t)(ctx->V[i] * 1000.0);
+    if (V_i32_out)  // K*K values: host (numpy: (V * _SMOOTH_COST_PRECISION).astype(intc))
+        for (int i = 0; i < K * K; ++i) V_i32_out[i] = (int32_t)(ctx->V[i] * ctx->sprec);
     return PHMRF_OK;
 }
 
 // ---------------------------------------------------------------- phase B
 int phmrf_set_labels(phmrf_region *r, const int32_t *labels_window) {
     if (!r || !labels_window) return PHMRF_E_INVALID;
-    const int K = r->ctx->K;
-    for (int64_t i = 0; i < r->n_window; ++i)
-        if (labels_window[i] < 0 || labels_window[i] >= K) {
-            set_error("phmrf_set_labels: label out of range at node " + std::to_string(i));
-            return PHMRF_E_INVALID;
-        }
     int rc = set_device(r->ctx);
     if (rc) return rc;
     PHMRF_CUDA(cudaMemcpyAsync(r->d_labels, labels_window, sizeof(int32_t) * r->n_window, cudaMemcpyHostToDevice,
                                r->stream));
+    // range check on the device (a host loop over 4e7 labels costs more than the copy)
+    long long first_bad = -1;
+    if ((rc = launch_check_labels(r->d_labels, r->n_window, r->ctx->K, r->d_badlabel, r->stream)) != PHMRF_OK) return rc;
+    PHMRF_CUDA(cudaMemcpyAsync(&first_bad, r->d_badlabel, sizeof(long long), cudaMemcpyDeviceToHost, r->stream));
     PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+    if (first_bad >= 0) {
+        r->have_labels = false;
+        set_error("phmrf_set_labels: label out of range at node " + std::to_string(first_bad));
+        return PHMRF_E_INVALID;
+    }
     r->have_labels = true;
     return PHMRF_OK;
 }
@@ -692,6 +731,11 @@ static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, boo
     EstepArgs a;
     a.X_soa = r->d_X;
     a.logp = r->d_logp;
+    a.rowmax = r->d_rowmax;
+    if (!r->have_rowmax) {  // a log-likelihood the quantise kernel has not seen
+        if ((rc = launch_rowmax(r->d_logp, r->n, ctx->K, r->d_rowmax, nullptr, r->stream)) != PHMRF_OK) return rc;
+        r->have_rowmax = true;
+    }
     a.labels = r->d_labels;
     a.nbr_id = r->d_nbr_id;
     a.nbr_w = r->d_nbr_w;
@@ -791,11 +835,15 @@ int phmrf_set_logprob(phmrf_region *r, const double *logprob) {
     if (r->n > 0) {
         if ((rc = ensure_scratch(r, r->n * K)) != PHMRF_OK) return rc;
         PHMRF_CUDA(cudaMemcpyAsync(r->d_scratch, logprob, sizeof(double) * r->n * K, cudaMemcpyHostToDevice, r->stream));
-        if ((rc = launch_aos_to_soa_k(r->d_scratch, r->d_logp, r->n, K, r->ld, r->stream)) != PHMRF_OK) return rc;
-        PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+        if ((rc = launch_logp_from_aos(r->d_scratch, r->d_logp, r->n, K, r->stream)) != PHMRF_OK) return rc;
     }
+    // max|logp| (the data term of the down-weight factor) and the per-node maxima follow the new array
+    PHMRF_CUDA(cudaMemsetAsync(r->d_absmax, 0, sizeof(unsigned long long), r->stream));
+    if ((rc = launch_rowmax(r->d_logp, r->n, K, r->d_rowmax, r->d_absmax, r->stream)) != PHMRF_OK) return rc;
+    PHMRF_CUDA(cudaStreamSynchronize(r->stream));
     r->have_logp = true;
     r->have_unary = false;
+    r->have_rowmax = true;
     return PHMRF_OK;
 }
 

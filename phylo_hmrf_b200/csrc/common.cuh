@@ -30,37 +30,57 @@ __host__ __device__ constexpr int n_stat_features(int D) { return 1 + D + D * (D
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Log-likelihood layout in HBM: tile-major, 32 nodes per tile, KP = logp_rows(K) state rows of
+// 32 doubles per tile, the node column XOR-swizzled by the state row:
+//   (k, i)  ->  ((i / 32) * KP + k) * 32 + ((i % 32) ^ ((k % 8) * 4))
+// One tile (KP * 256 bytes) is contiguous, so phase B fetches it with ONE bulk copy
+// (cp.async.bulk) straight into shared memory, where the swizzle makes both access patterns
+// conflict free: a lane per node along a row (per-node warps) and the FP64 mma operand
+// fragments (8 states x 4 nodes; tools/swizzle_check.py).  The XOR acts on multiples of 4,
+// so groups of 4 consecutive nodes stay contiguous (the emission kernel's 128-bit stores).
+__host__ __device__ __forceinline__ int64_t lp_index(int k, int64_t i, int KP) {
+    return ((i >> 5) * KP + k) * 32 + ((i & 31) ^ ((k & 7) << 2));
+}
+
 // ---- phase A (kernels_a.cu) -----------------------------------------------------------
 // X_aos [n,D] row-major -> X_soa [D][ld]
 int launch_aos_to_soa(const double *X_aos, double *X_soa, int64_t n, int D, int64_t ld, cudaStream_t s);
-// [n,K] row-major -> [K][ld]
-int launch_aos_to_soa_k(const double *aos, double *soa, int64_t n, int K, int64_t ld, cudaStream_t s);
-// logp [K][ld] -> out [n,K] row-major (also used for posteriors)
+// [K][ld] -> out [n,K] row-major (posteriors, pairwise potential)
 int launch_soa_to_aos(const double *soa, double *aos, int64_t n, int K, int64_t ld, cudaStream_t s);
+// log-likelihood: host order [n,K] row-major <-> the tiled device layout (lp_index)
+int launch_logp_from_aos(const double *aos, double *logp, int64_t n, int K, cudaStream_t s);
+int launch_logp_to_aos(const double *logp, double *aos, int64_t n, int K, cudaStream_t s);
 // emission: logp[k][i] for i<n, block maxima of |logp| folded into *absmax_bits (uint64 bit
 // pattern of a non-negative double, atomicMax).
 int launch_emit(const double *X_soa, int64_t n, int64_t ld, int D, int K, const double *model_global,
                 double *logp, unsigned long long *absmax_bits, int sm_count, cudaStream_t s);
+// per-node maximum over the states (phase B's soft-max shift); the quantise kernel writes it
+// on its way, this is the stand-alone form for a caller-supplied log-likelihood
+int launch_rowmax(const double *logp, int64_t n, int K, double *rowmax, unsigned long long *absmax_bits,
+                  cudaStream_t s);
+int launch_check_labels(const int32_t *labels, int64_t n, int K, long long *first_bad, cudaStream_t s);
 int launch_fill(double *p, double v, int64_t count, cudaStream_t s);
 // rows of the log-likelihood matrix: K rounded up to the 8-state tiles of the pipeline kernel;
 // the padding rows hold kLogpPad for the lifetime of a region
-inline int logp_rows(int K) { return (K + 7) / 8 * 8; }
+__host__ __device__ inline int logp_rows(int K) { return (K + 7) / 8 * 8; }
 constexpr double kLogpPad = -1.0e6;
+int launch_logp_init(double *logp, int64_t ld, int K, cudaStream_t s);
 // dwf = max(absmax_u, wmax*vmax) + 1e-10 unless dwf_in > 0; written to *dwf_dev.
 int launch_dwf(const unsigned long long *absmax_bits, double wmax, double vmax, double dwf_in, double *dwf_dev,
                cudaStream_t s);
-// unary_i32[i*K+k] = trunc(((-logp[k][i])/dwf)*1e5); boundary entries appended to blist.
-int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, const double *dwf_dev, double tol,
-                          int32_t *unary, long long *blist, long long bcap, unsigned long long *bcount,
-                          int sm_count, cudaStream_t s);
-// w_i32[e] = trunc((w[e]/dwf)*1e3)
-int launch_quantise_edges(const double *w, int64_t E, const double *dwf_dev, int32_t *w_i32, cudaStream_t s);
+// unary_i32[i*K+k] = trunc(((-logp[k][i])/dwf)*uprec); boundary entries appended to blist;
+// rowmax[i] = max_k logp[k][i]; and, in the same launch, w_i32[e] = trunc((w[e]/dwf)*wprec)
+// for the E edge weights (edge_w == nullptr skips it).
+int launch_quantise(const double *logp, int64_t n, int K, const double *dwf_dev, double tol, double uprec,
+                    int32_t *unary, double *rowmax, long long *blist, long long bcap, unsigned long long *bcount,
+                    const double *edge_w, int64_t E, double wprec, int32_t *w_i32, int sm_count, cudaStream_t s);
 int launch_argmin_unary(const int32_t *unary, int64_t n, int K, int32_t *labels, cudaStream_t s);
 
 // ---- phase B (kernels_b.cu) -----------------------------------------------------------
 struct EstepArgs {
     const double *X_soa;      // [D][ld]
-    const double *logp;       // [K][ld]
+    const double *logp;       // tiled [n/32][KP][32], see lp_index
+    const double *rowmax;     // [ld] max_k logp (pipeline kernel only)
     const int32_t *labels;    // [n_window]
     const int32_t *nbr_id;    // [W][ld] window-local neighbour id, -1 = none
     const double *nbr_w;      // [W][ld] edge weight per slot
@@ -85,6 +105,8 @@ int launch_nbr_g(const int32_t *nbr_id, const double *nbr_w, double *nbr_g, int6
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s);
 // Warp-specialised pipeline (kernels_b2.cu); *handled=false when the shape is outside its range.
 int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);
+// Bulk-copy pipeline (kernels_b3.cu), the default fast path; same contract.
+int launch_estep_bulk(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);
 // Fold per-block partials into stats_out (defined in kernels_b.cu).
 int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, double *stats_out, cudaStream_t s);
 

@@ -31,8 +31,58 @@ int launch_aos_to_soa(const double *X_aos, double *X_soa, int64_t n, int D, int6
     return PHMRF_OK;
 }
 
-int launch_aos_to_soa_k(const double *aos, double *soa, int64_t n, int K, int64_t ld, cudaStream_t s) {
-    return launch_aos_to_soa(aos, soa, n, K, ld, s);
+// host order [n,K] <-> tiled log-likelihood (lp_index): one warp per 32-node tile, staged
+// through shared memory so that both sides stay coalesced (one-off per host read-back / upload)
+template <bool TO_AOS>
+__global__ void logp_convert_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n, int K) {
+    extern __shared__ double cv_tile[];  // [warps][32*K]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tile = cv_tile + (size_t)warp * 32 * K;
+    const int KP = logp_rows(K);
+    const int64_t n_tiles = (n + 31) >> 5;
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; t < n_tiles;
+         t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t base = t << 5;
+        const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+        if (TO_AOS) {
+            for (int k = 0; k < K; ++k)
+                if (lane < cnt) tile[lane * K + k] = src[lp_index(k, base + lane, KP)];
+            __syncwarp();
+            for (int e = lane; e < cnt * K; e += 32) dst[base * K + e] = tile[e];
+        } else {
+            for (int e = lane; e < cnt * K; e += 32) tile[e] = src[base * K + e];
+            __syncwarp();
+            for (int k = 0; k < K; ++k)
+                if (lane < cnt) dst[lp_index(k, base + lane, KP)] = tile[lane * K + k];
+        }
+        __syncwarp();
+    }
+}
+
+template <bool TO_AOS>
+static int launch_logp_convert(const double *src, double *dst, int64_t n, int K, cudaStream_t s) {
+    if (n == 0) return PHMRF_OK;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 32 * K * 8 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 32 * K * 8;
+    if (smem > 200 * 1024) {
+        set_error("n_states too large for the layout conversion tile");
+        return PHMRF_E_UNSUPPORTED;
+    }
+    auto kern = logp_convert_kernel<TO_AOS>;
+    if (smem > 48 * 1024) PHMRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = ((n + 31) / 32 + warps - 1) / warps;
+    kern<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), warps * 32, smem, s>>>(src, dst, n, K);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+int launch_logp_from_aos(const double *aos, double *logp, int64_t n, int K, cudaStream_t s) {
+    return launch_logp_convert<false>(aos, logp, n, K, s);
+}
+int launch_logp_to_aos(const double *logp, double *aos, int64_t n, int K, cudaStream_t s) {
+    return launch_logp_convert<true>(logp, aos, n, K, s);
 }
 
 // [K][ld] -> [n][K] through a 32x32 shared-memory tile so both sides stay coalesced.
@@ -91,9 +141,10 @@ __device__ __forceinline__ unsigned long long abs_bits(double v) {
 }
 
 template <int D, bool SMEM_MODEL, int NPT>
-__global__ void __launch_bounds__(NPT == 8 ? 128 : 256) emit_kernel(const double *__restrict__ Xs, int64_t n, int64_t ld, int K,
+__global__ void __launch_bounds__(256) emit_kernel(const double *__restrict__ Xs, int64_t n, int64_t ld, int K,
                                                     const double *__restrict__ model, double *__restrict__ logp,
                                                     unsigned long long *absmax_bits) {
+    static_assert(NPT == 4, "the tiled log-likelihood layout keeps groups of 4 nodes contiguous");
     constexpr int PS = model_stride(D);
     constexpr int PSs = (PS + 1) & ~1;  // even stride: every state starts 16-byte aligned
     extern __shared__ __align__(16) double smodel[];
@@ -105,6 +156,7 @@ __global__ void __launch_bounds__(NPT == 8 ? 128 : 256) emit_kernel(const double
         __syncthreads();
     }
     unsigned long long amax = 0ull;
+    const int KP = logp_rows(K);
     const int64_t n_groups = ld / NPT;  // ld is a multiple of 64; the pad region holds zeros
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_groups;
          p += (int64_t)gridDim.x * blockDim.x) {
@@ -157,9 +209,11 @@ __global__ void __launch_bounds__(NPT == 8 ? 128 : 256) emit_kernel(const double
             double l[NPT];
 #pragma unroll
             for (int u = 0; u < NPT; ++u) l[u] = -acc[u];
+            // tiled layout (lp_index): NPT consecutive nodes stay contiguous under the swizzle
+            double *dst = logp + lp_index(k, i0, KP);
 #pragma unroll
             for (int u = 0; u < NPT; u += 2)
-                *reinterpret_cast<double2 *>(logp + k * ld + i0 + u) = make_double2(l[u], l[u + 1]);
+                *reinterpret_cast<double2 *>(dst + u) = make_double2(l[u], l[u + 1]);
 #pragma unroll
             for (int u = 0; u < NPT; ++u) {
                 const unsigned long long b = (i0 + u < n) ? abs_bits(l[u]) : 0ull;
@@ -279,15 +333,19 @@ __device__ __forceinline__ double div_by_dwf(double u, double dwf, double y) {
     return __fma_rn(r1, y, q1);
 }
 
-// One warp owns 32 consecutive nodes: it reads their K log-likelihood rows (256 B each,
-// coalesced), converts, stages the 32 x K integers in its own shared-memory tile and streams
-// them out as one contiguous 128*K-byte run.  No block-wide barrier: the warps of a CTA are
-// independent, so loads of one overlap stores of another.
-__global__ void __launch_bounds__(256, 4) quantise_unary_kernel(const double *__restrict__ logp, int64_t n, int64_t ld,
-                                                              int K, const double *__restrict__ dwf_dev, double tol,
-                                                              int32_t *__restrict__ unary,
-                                                              long long *__restrict__ blist, long long bcap,
-                                                              unsigned long long *bcount) {
+// One warp owns 32 consecutive nodes (one tile of the log-likelihood layout): it reads the K
+// state rows of the tile (256 B each, coalesced), converts, stages the 32 x K integers in its
+// own shared-memory tile and streams them out as one contiguous 128*K-byte run.  No block-wide
+// barrier: the warps of a CTA are independent, so loads of one overlap stores of another.
+// On the way it writes the per-node maximum over the states (phase B's soft-max shift; the
+// FP64 pipe idles in this HBM-bound kernel), and the same launch converts the edge weights
+// (pygco converts them on every call because dwf changes with the model).
+__global__ void __launch_bounds__(256, 4) quantise_kernel(const double *__restrict__ logp, int64_t n, int K,
+                                                          const double *__restrict__ dwf_dev, double tol, double uprec,
+                                                          int32_t *__restrict__ unary, double *__restrict__ rowmax,
+                                                          long long *__restrict__ blist, long long bcap,
+                                                          unsigned long long *bcount, const double *__restrict__ edge_w,
+                                                          int64_t E, double wprec, int32_t *__restrict__ w_i32) {
     extern __shared__ __align__(16) int32_t tile_all[];  // [warps][32][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int32_t *tile = tile_all + (size_t)warp * 32 * K;
@@ -296,6 +354,7 @@ __global__ void __launch_bounds__(256, 4) quantise_unary_kernel(const double *__
     // the refinement needs a finite, normal reciprocal; otherwise use the plain division
     const bool fast_div = (dwf > 1e-290) && (dwf < 1e290);
     constexpr int U = 6;  // states in flight per thread
+    const int KP = logp_rows(K);
     const int64_t n_tiles = (n + 31) >> 5;
     const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; t < n_tiles; t += wstride) {
@@ -303,19 +362,25 @@ __global__ void __launch_bounds__(256, 4) quantise_unary_kernel(const double *__
         const int64_t i = base + lane;
         const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
         if (i < n) {
-            const double *src = logp + i;
+            const double *src = logp + t * KP * 32;
+            double rmax = -INFINITY;
             for (int k0 = 0; k0 < K; k0 += U) {
                 double u[U];
 #pragma unroll
-                for (int q = 0; q < U; ++q) u[q] = (k0 + q) < K ? -src[(int64_t)(k0 + q) * ld] : 0.0;
+                for (int q = 0; q < U; ++q) {
+                    const int k = k0 + q;
+                    u[q] = k < K ? src[k * 32 + (lane ^ ((k & 7) << 2))] : -INFINITY;
+                }
 #pragma unroll
                 for (int q = 0; q < U; ++q) {
                     const int k = k0 + q;
                     if (k < K) {
-                        const double quo = fast_div ? div_by_dwf(u[q], dwf, ydwf) : __ddiv_rn(u[q], dwf);
-                        const double tq = __dmul_rn(quo, 100000.0);
+                        rmax = fmax(rmax, u[q]);
+                        const double nu = -u[q];
+                        const double quo = fast_div ? div_by_dwf(nu, dwf, ydwf) : __ddiv_rn(nu, dwf);
+                        const double tq = __dmul_rn(quo, uprec);
                         tile[lane * K + k] = __double2int_rz(tq);
-                        // |tq| <= 1e5: nearest integer through the 2^52+2^51 constant
+                        // |tq| <= uprec < 2^51: nearest integer through the 2^52+2^51 constant
                         const double r = (tq + 6755399441055744.0) - 6755399441055744.0;
                         const double dist = fabs(tq - r);
                         if (dist <= tol || dist <= tol * fabs(tq)) {
@@ -325,6 +390,7 @@ __global__ void __launch_bounds__(256, 4) quantise_unary_kernel(const double *__
                     }
                 }
             }
+            rowmax[i] = rmax;
         }
         __syncwarp();
         int32_t *dst = unary + base * K;
@@ -338,13 +404,22 @@ __global__ void __launch_bounds__(256, 4) quantise_unary_kernel(const double *__
         }
         __syncwarp();
     }
+    // edge weights: w_i32[e] = trunc((w[e] / dwf) * wprec)
+    if (edge_w != nullptr) {
+        const int64_t tstride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += tstride) {
+            const double w = edge_w[e];
+            const double quo = fast_div ? div_by_dwf(w, dwf, ydwf) : __ddiv_rn(w, dwf);
+            w_i32[e] = __double2int_rz(__dmul_rn(quo, wprec));
+        }
+    }
 }
 
-int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, const double *dwf_dev, double tol,
-                          int32_t *unary, long long *blist, long long bcap, unsigned long long *bcount,
-                          int sm_count, cudaStream_t s) {
+int launch_quantise(const double *logp, int64_t n, int K, const double *dwf_dev, double tol, double uprec,
+                    int32_t *unary, double *rowmax, long long *blist, long long bcap, unsigned long long *bcount,
+                    const double *edge_w, int64_t E, double wprec, int32_t *w_i32, int sm_count, cudaStream_t s) {
     PHMRF_CUDA(cudaMemsetAsync(bcount, 0, sizeof(unsigned long long), s));
-    if (n == 0) return PHMRF_OK;
+    if (n == 0 && (edge_w == nullptr || E == 0)) return PHMRF_OK;
     int warps = 8;
     while (warps > 1 && (size_t)warps * 32 * K * 4 > 64 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * 32 * K * 4;
@@ -353,29 +428,88 @@ int launch_quantise_unary(const double *logp, int64_t n, int64_t ld, int K, cons
         return PHMRF_E_UNSUPPORTED;
     }
     if (smem > 48 * 1024)
-        PHMRF_CUDA(cudaFuncSetAttribute(quantise_unary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PHMRF_CUDA(cudaFuncSetAttribute(quantise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (n + 31) / 32;
-    const int64_t blocks = (n_tiles + warps - 1) / warps;
+    int64_t blocks = (n_tiles + warps - 1) / warps;
+    const int64_t eblocks = edge_w ? (E + warps * 32 - 1) / (warps * 32) : 0;
+    if (eblocks > blocks) blocks = eblocks;
     const int64_t cap = (int64_t)sm_count * 4;  // one resident wave (4 CTAs/SM at <= 64 registers)
-    const int grid = (int)(blocks < cap ? blocks : cap);
-    quantise_unary_kernel<<<grid, warps * 32, smem, s>>>(logp, n, ld, K, dwf_dev, tol, unary, blist, bcap, bcount);
+    const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+    quantise_kernel<<<grid, warps * 32, smem, s>>>(logp, n, K, dwf_dev, tol, uprec, unary, rowmax, blist, bcap, bcount,
+                                                    edge_w, edge_w ? E : 0, wprec, w_i32);
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     return PHMRF_OK;
 }
 
-__global__ void quantise_edges_kernel(const double *__restrict__ w, int64_t E, const double *__restrict__ dwf_dev,
-                                      int32_t *__restrict__ out) {
-    const double dwf = dwf_dev[0];
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
-        out[e] = __double2int_rz(__dmul_rn(__ddiv_rn(w[e], dwf), 1000.0));
+// per-node maximum over the states for a log-likelihood the quantise kernel has not seen
+// (phmrf_set_logprob followed directly by the E-step); optionally max|logp| as well
+__global__ void rowmax_kernel(const double *__restrict__ logp, int64_t n, int K, double *__restrict__ rowmax,
+                              unsigned long long *absmax_bits) {
+    const int KP = logp_rows(K);
+    unsigned long long amax = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double m = -INFINITY;
+        for (int k = 0; k < K; ++k) {
+            const double v = logp[lp_index(k, i, KP)];
+            m = fmax(m, v);
+            const unsigned long long b = abs_bits(v);
+            amax = b > amax ? b : amax;
+        }
+        rowmax[i] = m;
+    }
+    if (absmax_bits != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, amax, o);
+            amax = other > amax ? other : amax;
+        }
+        if ((threadIdx.x & 31) == 0 && amax) atomicMax(absmax_bits, amax);
+    }
 }
 
-int launch_quantise_edges(const double *w, int64_t E, const double *dwf_dev, int32_t *w_i32, cudaStream_t s) {
-    if (E == 0) return PHMRF_OK;
-    int64_t blocks = (E + 255) / 256;
-    int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    quantise_edges_kernel<<<grid, 256, 0, s>>>(w, E, dwf_dev, w_i32);
+int launch_rowmax(const double *logp, int64_t n, int K, double *rowmax, unsigned long long *absmax_bits,
+                  cudaStream_t s) {
+    if (n == 0) return PHMRF_OK;
+    const int64_t blocks = (n + 255) / 256;
+    rowmax_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, s>>>(logp, n, K, rowmax, absmax_bits);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+// labels must lie in [0, K): *first_bad = smallest offending index, -1 when all are valid
+__global__ void check_labels_kernel(const int32_t *__restrict__ labels, int64_t n, int K, long long *first_bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = labels[i];
+        if (l < 0 || l >= K) atomicMin((unsigned long long *)first_bad, (unsigned long long)i);
+    }
+}
+
+int launch_check_labels(const int32_t *labels, int64_t n, int K, long long *first_bad, cudaStream_t s) {
+    PHMRF_CUDA(cudaMemsetAsync(first_bad, 0xff, sizeof(long long), s));  // -1 == max as unsigned
+    if (n == 0) return PHMRF_OK;
+    const int64_t blocks = (n + 255) / 256;
+    check_labels_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, s>>>(labels, n, K, first_bad);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+// zero the log-likelihood buffer and set the padding state rows K..KP-1 of every tile
+__global__ void logp_init_kernel(double *__restrict__ logp, int64_t ld, int K, int KP, double pad) {
+    const int64_t total = (ld >> 5) * KP * 32;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)((e >> 5) % KP);
+        logp[e] = k < K ? 0.0 : pad;
+    }
+}
+
+int launch_logp_init(double *logp, int64_t ld, int K, cudaStream_t s) {
+    const int KP = logp_rows(K);
+    const int64_t total = (ld >> 5) * KP * 32;
+    const int64_t blocks = (total + 255) / 256;
+    logp_init_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, s>>>(logp, ld, K, KP, kLogpPad);
     count_launch();
     PHMRF_CUDA(cudaGetLastError());
     return PHMRF_OK;

@@ -16,6 +16,8 @@
 // Accumulators live in registers for the whole kernel; block partials are reduced in a
 // fixed order (deterministic) and a final kernel folds them and unpacks the symmetric
 // scatter into the reference's [K], [K,d], [K,d,d] layout.
+#include <cstdlib>
+
 #include "estep_common.cuh"
 
 namespace phmrf {
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
     double c_pair = 0.0, c_pwn = 0.0, c_un = 0.0;
 
     const int K = a.K, W = a.W;
+    const int KP = logp_rows(K);
     const int64_t n = a.n, ld = a.ld;
     const int64_t n_tiles = (n + 31) >> 5;
     const int64_t warp_global = (int64_t)blockIdx.x * wpb + warp;
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
             const int64_t t2 = t + warp_stride;
             if (t2 < n_tiles) {
                 const int64_t i2 = t2 << 5;
-                for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (q >> 1) * ld + i2 + (q & 1) * 16);
+                for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (t2 * KP + (q >> 1)) * 32 + (q & 1) * 16);
                 for (int q = lane; q < 2 * D; q += 32) prefetch_l2(a.X_soa + (q >> 1) * ld + i2 + (q & 1) * 16);
                 for (int q = lane; q < 2 * W; q += 32) prefetch_l2(a.nbr_w + (q >> 1) * ld + i2 + (q & 1) * 16);
                 for (int q = lane; q < W; q += 32) prefetch_l2(a.nbr_id + q * ld + i2);
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
 
         const int li = a.labels[a.own_offset + i];
         const int pos_li = (li / TK) * TKs + (li % TK);
-        const double lp_li = a.logp[li * ld + i];
+        const double lp_li = a.logp[lp_index(li, i, KP)];
 
         // ---------------- node phase ----------------
         double pc = 0.0, pwn_log = 0.0, esum = 0.0;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
 #pragma unroll
                 for (int ii = 0; ii < TK; ++ii) {
                     const int k = ktile * TK + ii;
-                    if (k < K) e[ii] = a.logp[k * ld + i];
+                    if (k < K) e[ii] = a.logp[lp_index(k, i, KP)];
                 }
 #pragma unroll
                 for (int ii = 0; ii < TK; ++ii) {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                     if (k < K) {
                         const double sv = Prow[ktile * TKs + ii];
                         const double pp = a.potts ? wtot - fabs(sv) : sv;
-                        amax = fmax(amax, a.logp[k * ld + i] - pp);
+                        amax = fmax(amax, a.logp[lp_index(k, i, KP)] - pp);
                     }
                 }
             }
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) estep_kernel(EstepArgs a, int nkt
                     if (ii < TK && k < K) {
                         const double sv = Prow[ktile * TKs + ii];
                         const double pp = a.potts ? wtot - fabs(sv) : sv;
-                        e = exp((a.logp[k * ld + i] - pp) - amax);
+                        e = exp((a.logp[lp_index(k, i, KP)] - pp) - amax);
                         if (a.pp_soa != nullptr && first_pass && valid) a.pp_soa[k * ld + i] = pp;
                     }
                     esum += e;
@@ -494,7 +497,12 @@ int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s) {
     }
     if (!a.force_general) {
         bool handled = false;
-        int rc = launch_estep_pipe(a, sm_count, s, &handled);
+        // PHMRF_ESTEP_KERNEL=r1 selects the round-1 pipeline (kernels_b2.cu), kept for A/B timing
+        static const bool use_r1 = [] {
+            const char *v = getenv("PHMRF_ESTEP_KERNEL");
+            return v != nullptr && v[0] == 'r' && v[1] == '1';
+        }();
+        int rc = use_r1 ? launch_estep_pipe(a, sm_count, s, &handled) : launch_estep_bulk(a, sm_count, s, &handled);
         if (rc != PHMRF_OK || handled) return rc;
     }
     switch (a.D) {

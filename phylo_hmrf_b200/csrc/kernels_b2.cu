@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(pipe_threads(P), 1) estep_mma_kernel(EstepArgs
                 const int64_t T2 = T + tile_stride_g;
                 if (T2 < n_tiles) {
                     const int64_t i2 = T2 * kTileNodes;
-                    for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (q >> 1) * ld + i2 + (q & 1) * 16);
+                    for (int q = lane; q < 2 * K; q += 32) prefetch_l2(a.logp + (T2 * KP + (q >> 1)) * 32 + (q & 1) * 16);
                     if (lane < 2 * D) prefetch_l2(a.X_soa + (lane >> 1) * ld + i2 + (lane & 1) * 16);
                     if (lane < 2 * W) prefetch_l2(a.nbr_w + (lane >> 1) * ld + i2 + (lane & 1) * 16);
                     if (lane >= 16 && lane - 16 < 2 * W)
@@ -175,18 +175,17 @@ __global__ void __launch_bounds__(pipe_threads(P), 1) estep_mma_kernel(EstepArgs
                 }
 #pragma unroll
                 for (int s = 0; s < kFastSlots; ++s) lab[s] = jid[s] >= 0 ? a.labels[jid[s]] : -1;
-                lp_li = a.logp[li * ld + i];
+                lp_li = a.logp[lp_index(li, i, KP)];
             }
             // the node's log-likelihood row (registers; issued before the neighbour arithmetic so
             // that its latency overlaps)
             double e[KP];
             {
-                const double *pk = a.logp + i;
+                const double *pk = a.logp + (i >> 5) * (KP * 32);
+                const int col = (int)(i & 31);
 #pragma unroll
-                for (int q = 0; q < KP; ++q) {  // rows K..KP-1 hold kLogpPad (phmrf_region_create)
-                    e[q] = *pk;
-                    pk += ld;
-                }
+                for (int q = 0; q < KP; ++q)  // rows K..KP-1 hold kLogpPad (phmrf_region_create)
+                    e[q] = pk[q * 32 + (col ^ ((q & 7) << 2))];
             }
             int all_neg = -1;  // sign bit stays set while no slot holds a neighbour
             double pc = 0.0;   // sum over the incident edges of V[l_nbr, l_i] * w

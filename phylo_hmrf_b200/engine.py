@@ -35,6 +35,17 @@ class Model:
             raise ValueError("'covars' must be symmetric, positive-definite")
         check(rc)
 
+    def set_quantiser(self, unary_precision=100000, pairwise_precision=1000, smooth_precision=100):
+        """Scale factors of pygco's float->int conversion (see phmrf_set_quantiser); the defaults
+        are pygco's _UNARY_FLOAT_PRECISION / _PAIRWISE_FLOAT_PRECISION / _SMOOTH_COST_PRECISION."""
+        check(_lib.lib().phmrf_set_quantiser(self._h, float(unary_precision), float(pairwise_precision),
+                                             float(smooth_precision)))
+
+    def quantiser(self):
+        u, w, v = C.c_double(), C.c_double(), C.c_double()
+        check(_lib.lib().phmrf_get_quantiser(self._h, C.byref(u), C.byref(w), C.byref(v)))
+        return u.value, w.value, v.value
+
     def region(self, X, edge_ids, edge_w, n_window=None, own_offset=0, stream=None):
         return Region(self, X, edge_ids, edge_w, n_window, own_offset, stream)
 

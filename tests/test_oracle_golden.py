@@ -123,7 +123,8 @@ def test_density_cholesky_fallback():
 
 
 def test_quantiser_contract():
-    """pygco contract (third-party, parity unpinned): divide, multiply, truncate toward zero."""
+    """pygco contract (third-party, parity unpinned): divide, multiply, truncate toward zero.
+    Scale factors 1e5 (unary), 1e3 (edge weights), 1e2 (V): pygco's "pairwise * smooth = unary"."""
     unary = np.array([[0.0, 3.0, -1.5], [2.999999, 1.0, 0.5]])
     w = np.array([0.9, 0.25])
     V = orc.pairwise_potential(3, 2.0)
@@ -132,7 +133,11 @@ def test_quantiser_contract():
     assert u_i.dtype == np.intc and u_i.flags.c_contiguous
     assert u_i[0, 1] == 99999 and u_i[0, 0] == 0
     assert u_i[0, 2] == -49999  # truncation toward zero, not floor
-    assert np.array_equal(V_i, np.array([[0, 2000, 2000], [2000, 0, 2000], [2000, 2000, 0]]))
+    assert np.array_equal(V_i, np.array([[0, 200, 200], [200, 0, 200], [200, 200, 0]]))
+    assert orc.PYGCO_PAIRWISE_FLOAT_PRECISION * orc.PYGCO_SMOOTH_COST_PRECISION == orc.PYGCO_UNARY_FLOAT_PRECISION
+    # the scale factors are parameters (a maintainer can match another pygco build)
+    _, w_k, V_k, _ = orc.pygco_quantise(unary, w, V, pairwise_precision=100, smooth_precision=1000)
+    assert np.array_equal(V_k, 10 * V_i) and np.array_equal(w_k, np.array([int(0.9 / dwf * 100), int(0.25 / dwf * 100)]))
     assert np.array_equal(w_i, np.array([int(0.9 / dwf * 1000), int(0.25 / dwf * 1000)]))
     # weights dominate the down-weight factor when the unary is small
     _, _, _, dwf2 = orc.pygco_quantise(unary * 1e-3, w, V)
