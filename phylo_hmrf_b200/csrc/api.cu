@@ -3,6 +3,7 @@
 // extern "C" entry points declared in include/phmrf.h.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -57,6 +58,12 @@ struct phmrf_region {
     int32_t *d_nbr_id = nullptr; // [W][ld]
     double *d_nbr_w = nullptr;   // [W][ld]
     double *d_nbr_g = nullptr;   // [W][ld] exp(beta*w), built on first use for (g_beta, g_weighted)
+    // implicit-grid form (phmrf_region_create_grid): forward-edge {w, exp(beta*w)} per window node
+    double2 *d_fwd = nullptr;    // [4][ldw]
+    int64_t ldw = 0, own_start_gid = 0, grid_n2 = 0, grid_rows = 0;
+    int grid_kind = -1, grid_nn = 0;
+    double fwd_beta = 0.0;
+    int fwd_weighted = -1;
     double g_beta = 0.0;
     int g_weighted = -1;
     double *d_edge_w = nullptr;  // [E]
@@ -478,6 +485,16 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
         return cuda_fail(err, "memset X", __FILE__, __LINE__);
     }
     TRY(launch_aos_to_soa(dXw + r->own_offset * D, r->d_X, n_own, D, ld, r->stream));
+    // implicit-grid form of phase B: one {w, g} pair per forward edge of every window node up to the last owned one
+    r->grid_kind = kind;
+    r->grid_nn = num_neighbor;
+    r->grid_n2 = n2;
+    r->grid_rows = rows;
+    r->own_start_gid = own_start;
+    r->ldw = round_up(r->own_offset + n_own > 0 ? r->own_offset + n_own : 1, 64);
+    TRY(dev_alloc(r, &r->d_fwd, 4 * r->ldw));
+    TRY(launch_band_fwd(dXw, kind, n1, n2, num_neighbor, D, win_start, r->own_offset + n_own, beta1, r->ldw, r->d_fwd,
+                        r->stream));
     // max|w| lands in d_absmax[1] (free until the first quantise resets it as the boundary counter)
     TRY(launch_band_graph(dXw, kind, n1, n2, num_neighbor, D, win_start, own_start, own_end, n_window, beta1, ld,
                           r->d_nbr_id, r->d_nbr_w, r->d_edge_ids, r->d_edge_w, &n_edges, r->d_absmax + 1, r->stream));
@@ -542,6 +559,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     cudaFree(r->d_nbr_id);
     cudaFree(r->d_nbr_w);
     cudaFree(r->d_nbr_g);
+    cudaFree(r->d_fwd);
     cudaFree(r->d_edge_w);
     cudaFree(r->d_edge_wi);
     cudaFree(r->d_edge_ids);
@@ -763,21 +781,44 @@ static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, boo
     a.s_bound = ctx->beta * r->W * (estimate_type == 3 ? r->wmax : 1.0);
     a.nbr_g = nullptr;
     a.exp_beta = std::exp(ctx->beta);
+    a.fwd_wg = nullptr;
+    a.ldw = r->ldw;
+    a.grid_kind = -1;
+    a.grid_nn = r->grid_nn;
+    a.grid_n2 = r->grid_n2;
+    a.grid_rows = r->grid_rows;
+    a.own_start_gid = r->own_start_gid;
     if (ctx->potts && !force_general && !want_pp && r->W > 0 && std::fabs(a.s_bound) < 100.0) {
         // per-slot factors of the pipeline kernel: constant while beta and the weights are
         const int weighted = estimate_type == 3 ? 1 : 0;
-        if (!r->d_nbr_g) {
-            if ((rc = dev_alloc(r, &r->d_nbr_g, (int64_t)r->W * r->ld)) != PHMRF_OK) return rc;
-            r->g_weighted = -1;
+        // PHMRF_GRID_IMPLICIT=0 keeps grid-built regions on the explicit neighbour slots (A/B timing)
+        static const bool implicit_ok = [] {
+            const char *v = getenv("PHMRF_GRID_IMPLICIT");
+            return !(v != nullptr && v[0] == '0');
+        }();
+        if (r->d_fwd && implicit_ok) {
+            // region built from the grid geometry: implicit neighbours, each weight stored once
+            if (r->fwd_weighted != weighted || r->fwd_beta != ctx->beta) {
+                if ((rc = launch_fwd_factor(r->d_fwd, 4 * r->ldw, ctx->beta, weighted, r->stream)) != PHMRF_OK) return rc;
+                r->fwd_weighted = weighted;
+                r->fwd_beta = ctx->beta;
+            }
+            a.fwd_wg = r->d_fwd;
+            a.grid_kind = r->grid_kind;
+        } else {
+            if (!r->d_nbr_g) {
+                if ((rc = dev_alloc(r, &r->d_nbr_g, (int64_t)r->W * r->ld)) != PHMRF_OK) return rc;
+                r->g_weighted = -1;
+            }
+            if (r->g_weighted != weighted || r->g_beta != ctx->beta) {
+                if ((rc = launch_nbr_g(r->d_nbr_id, r->d_nbr_w, r->d_nbr_g, (int64_t)r->W * r->ld, ctx->beta, weighted,
+                                       r->stream)) != PHMRF_OK)
+                    return rc;
+                r->g_weighted = weighted;
+                r->g_beta = ctx->beta;
+            }
+            a.nbr_g = r->d_nbr_g;
         }
-        if (r->g_weighted != weighted || r->g_beta != ctx->beta) {
-            if ((rc = launch_nbr_g(r->d_nbr_id, r->d_nbr_w, r->d_nbr_g, (int64_t)r->W * r->ld, ctx->beta, weighted,
-                                   r->stream)) != PHMRF_OK)
-                return rc;
-            r->g_weighted = weighted;
-            r->g_beta = ctx->beta;
-        }
-        a.nbr_g = r->d_nbr_g;
     }
     PHMRF_CUDA(cudaMemsetAsync(r->d_flags, 0, sizeof(int), r->stream));
     return launch_estep(a, ctx->sm_count, r->stream);

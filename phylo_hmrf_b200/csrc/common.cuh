@@ -98,6 +98,14 @@ struct EstepArgs {
     double s_bound;           // upper bound of any neighbour weight sum: beta * W * max|w|
     const double *nbr_g;      // [W][ld] exp(beta * w) per slot (1 for an empty slot); pipeline kernel only
     double exp_beta;          // exp(beta)
+    // implicit-grid form (regions built by phmrf_region_create_grid): neighbours are fixed offsets
+    // from the row geometry, each edge weight is stored once, with its forward end
+    const double2 *fwd_wg;    // [4][ldw] per window node: {w, exp(beta*w)} of right, lower-left, lower, lower-right
+    int64_t ldw;
+    int grid_kind;            // 1 diagonal region (upper triangle), 0 rectangle, -1: explicit neighbour slots
+    int grid_nn;              // 8 or 4
+    int64_t grid_n2, grid_rows;
+    int64_t own_start_gid;    // region-global node id of the first owned node
 };
 // g[s][i] = exp(beta * (weighted ? w[s][i] : 1)) for occupied slots, 1 otherwise (kernels_b2.cu)
 int launch_nbr_g(const int32_t *nbr_id, const double *nbr_w, double *nbr_g, int64_t count, double beta, int weighted,
@@ -120,6 +128,11 @@ int launch_band_graph(const double *Xw_dev, int kind, long long n1, long long n2
                       long long own_start, long long own_end, long long n_window, double beta1, long long ld,
                       int32_t *nbr_id, double *nbr_w, long long *ids_dev, double *w_dev, long long *n_edges,
                       unsigned long long *wmax_bits, cudaStream_t s);
+
+// forward-edge weights of the window nodes [0, n_fw) (implicit-grid form of phase B)
+int launch_band_fwd(const double *Xw_dev, int kind, long long n1, long long n2, int nn, int D, long long win_start,
+                    long long n_fw, double beta1, long long ldw, double2 *fwd, cudaStream_t s);
+int launch_fwd_factor(double2 *fwd, long long count, double beta, int weighted, cudaStream_t s);
 
 // ---- probes (probe.cu) ----------------------------------------------------------------
 int run_probe(int which, double *out);

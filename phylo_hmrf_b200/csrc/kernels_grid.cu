@@ -217,7 +217,66 @@ __global__ void band_ell_kernel(Grid g, Band b, long long n_own, long long ld, i
     }
 }
 
+// Forward-edge weights of every window node up to the last owned one, for the implicit-grid
+// form of phase B: slot 0 = right, 1 = lower left, 2 = lower, 3 = lower right (ascending
+// neighbour id); .x = w = exp(-beta1 * d_ij) (0 where the neighbour is outside the region),
+// .y = the per-slot factor exp(beta * w), filled by fwd_factor_kernel.
+__global__ void band_fwd_kernel(Grid g, Band b, long long n_fw, long long ldw, int D, const double *__restrict__ Xw,
+                                double beta1, double2 *__restrict__ fwd) {
+    const bool tri = g.kind != 0;
+    const long long rows = tri ? g.n2 : g.n1, cols = g.n2;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_fw;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = b.win_start + t;
+        long long x, y;
+        node_xy(g, i, x, y);
+        const double *xi = Xw + t * D;
+        auto put = [&](int slot, long long a2, long long c2, bool use) {
+            double w = 0.0;
+            if (use && a2 >= 0 && a2 < rows && c2 >= 0 && c2 < cols && (!tri || a2 <= c2)) {
+                const long long j = node_id(g, a2, c2);
+                const bool halve = tri && x == y && a2 == c2;
+                w = exp(-beta1 * edge_distance(xi, Xw + (j - b.win_start) * D, D, halve));
+            }
+            fwd[slot * ldw + t] = make_double2(w, 1.0);
+        };
+        put(0, x, y + 1, true);
+        put(1, x + 1, y - 1, g.nn == 8);
+        put(2, x + 1, y, true);
+        put(3, x + 1, y + 1, g.nn == 8);
+    }
+}
+
+__global__ void fwd_factor_kernel(double2 *__restrict__ fwd, long long count, double beta, int weighted) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        double2 v = fwd[i];
+        v.y = exp(beta * (weighted ? v.x : 1.0));
+        fwd[i] = v;
+    }
+}
+
 }  // namespace
+
+int launch_band_fwd(const double *Xw_dev, int kind, long long n1, long long n2, int nn, int D, long long win_start,
+                    long long n_fw, double beta1, long long ldw, double2 *fwd, cudaStream_t s) {
+    if (n_fw <= 0) return PHMRF_OK;
+    Grid g{kind, n1, n2, nn};
+    Band b{win_start, 0, 0};
+    const int grid = (int)((n_fw + 255) / 256 < 148 * 16 ? (n_fw + 255) / 256 : 148 * 16);
+    band_fwd_kernel<<<grid, 256, 0, s>>>(g, b, n_fw, ldw, D, Xw_dev, beta1, fwd);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
+int launch_fwd_factor(double2 *fwd, long long count, double beta, int weighted, cudaStream_t s) {
+    if (count <= 0) return PHMRF_OK;
+    const long long blocks = (count + 255) / 256;
+    fwd_factor_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, s>>>(fwd, count, beta, weighted);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
 
 // Closed-form edge count of a dense region.
 long long grid_edge_count(int kind, long long n1, long long n2, int nn) {
