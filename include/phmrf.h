@@ -68,6 +68,17 @@ int phmrf_set_quantiser(phmrf_ctx *ctx, double unary_precision, double pairwise_
 int phmrf_get_quantiser(const phmrf_ctx *ctx, double *unary_precision, double *pairwise_precision,
                         double *smooth_precision);
 
+/* ------------------------------------------------------------------ host staging ------ */
+
+/* Page-locked host memory for the arrays that cross PCIe every EM iteration of a region: the
+ * integer unary / edge weights pygco hands to the graph cut (phylo_hmrf.py:496-498; device ->
+ * host) and the labels it returns (host -> device).  The reference holds these as ordinary NumPy
+ * arrays (pageable); copies to or from pageable memory are staged by the driver and serialise,
+ * copies to or from these buffers run at the link rate and overlap with kernels and with copies in
+ * the other direction.  Any entry point accepts either kind of pointer. */
+int phmrf_host_alloc(int64_t bytes, void **out);
+int phmrf_host_free(void *p);
+
 /* ------------------------------------------------------------------ region ------------ */
 
 /* Replaces the per-region inputs of _predict_posteriors (phylo_hmrf.py:297-322): X[s1:s2]

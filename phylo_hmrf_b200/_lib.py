@@ -33,6 +33,8 @@ _vp = C.c_void_p
 SIGNATURES = {
     "phmrf_abi_version": (C.c_int, []),
     "phmrf_last_error": (C.c_char_p, []),
+    "phmrf_host_alloc": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
+    "phmrf_host_free": (C.c_int, [_vp]),
     "phmrf_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "phmrf_ctx_destroy": (C.c_int, [_vp]),
     "phmrf_set_model": (C.c_int, [_vp, _c_double_p, _c_double_p, _c_double_p]),

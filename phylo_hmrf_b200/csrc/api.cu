@@ -137,6 +137,22 @@ int phmrf_abi_version(void) { return PHMRF_ABI_VERSION; }
 const char *phmrf_last_error(void) { return g_error.c_str(); }
 int64_t phmrf_launch_count(void) { return g_launches.load(); }
 
+int phmrf_host_alloc(int64_t bytes, void **out) {
+    if (!out || bytes < 0) {
+        set_error("phmrf_host_alloc: invalid arguments");
+        return PHMRF_E_INVALID;
+    }
+    *out = nullptr;
+    // portable: usable from every device's streams (one process may drive several regions)
+    PHMRF_CUDA(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocPortable));
+    return PHMRF_OK;
+}
+
+int phmrf_host_free(void *p) {
+    if (p) PHMRF_CUDA(cudaFreeHost(p));
+    return PHMRF_OK;
+}
+
 int phmrf_ctx_create(int device, int n_states, int n_features, phmrf_ctx **out) {
     if (!out || n_states < 1 || n_features < kMinFeatures || n_features > kMaxFeatures) {
         set_error("phmrf_ctx_create: need n_states>=1 and 1<=n_features<=12");

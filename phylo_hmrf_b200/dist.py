@@ -125,6 +125,31 @@ def assign_regions(region_sizes, world_size):
     return owner
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores NVML reports as local to the GPU (its NUMA node), so that
+    the page-locked staging buffers allocated afterwards sit behind the same PCIe root as the
+    device they feed.  One process per GPU all allocating on the default node is what limits the
+    host<->device copies of an 8-GPU run.  Returns the core list, or None when NVML or the
+    affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cores = [c for c in cores if c < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(set(cores) & allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def world_info():
     """(world_size, rank) of the initialised torch.distributed process group, else (1, 0)."""
     try:

@@ -16,6 +16,21 @@ import numpy as np
 from . import _lib
 from ._lib import PhmrfError, as_f64, check, dptr, i32ptr, i64ptr
 
+def pinned_empty(shape, dtype):
+    """NumPy array in page-locked host memory (phmrf_host_alloc): copies to and from it run at
+    the PCIe rate and overlap with kernels and with copies in the other direction.  The memory
+    is released when the array (and every view of it) is garbage collected."""
+    import weakref
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape, dtype=np.int64))
+    nbytes = max(1, count * dtype.itemsize)
+    p = C.c_void_p()
+    check(_lib.lib().phmrf_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_byte * nbytes).from_address(p.value)
+    weakref.finalize(buf, _lib.lib().phmrf_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
 class Model:
     """Device-side model state: means_ [K,d], _covars_ [K,d,d], edge_potential [K,K]."""
 
@@ -119,11 +134,22 @@ class Region:
         check(_lib.lib().phmrf_pairwise_potential(self._h, int(estimate_type), dptr(out)))
         return out
 
-    def quantise(self, dwf=0.0, tol=1e-9, want_unary=True, want_edges=True, boundary_cap=1 << 16):
-        """-> dict(unary_i32, w_i32, V_i32, dwf, boundary_idx, n_boundary)"""
+    def quantise(self, dwf=0.0, tol=1e-9, want_unary=True, want_edges=True, boundary_cap=1 << 16, staged=False):
+        """-> dict(unary_i32, w_i32, V_i32, dwf, boundary_idx, n_boundary)
+
+        staged=True returns the integer arrays as views of the region's own page-locked staging
+        buffers (allocated once, overwritten by the next staged call on this region): the
+        per-iteration product path, where the arrays go straight into the graph cut."""
         K = self.model.K
-        u = np.empty((self.n, K), dtype=np.int32) if want_unary else None
-        wi = np.empty(self.n_edges, dtype=np.int32) if want_edges else None
+        if staged:
+            if getattr(self, "_pin_unary", None) is None:
+                self._pin_unary = pinned_empty((self.n, K), np.int32)
+                self._pin_w = pinned_empty((self.n_edges,), np.int32)
+            u = self._pin_unary if want_unary else None
+            wi = self._pin_w if want_edges else None
+        else:
+            u = np.empty((self.n, K), dtype=np.int32) if want_unary else None
+            wi = np.empty(self.n_edges, dtype=np.int32) if want_edges else None
         Vi = np.empty((K, K), dtype=np.int32)
         d = C.c_double()
         nb = C.c_int64()
@@ -132,6 +158,13 @@ class Region:
                                         i64ptr(bl), int(boundary_cap), C.byref(nb)))
         m = min(int(nb.value), boundary_cap)
         return dict(unary_i32=u, w_i32=wi, V_i32=Vi, dwf=d.value, boundary_idx=bl[:m].copy(), n_boundary=int(nb.value))
+
+    def label_staging(self):
+        """Page-locked int32 buffer covering the label window: the graph cut writes its result here
+        (gco_cut_int(..., out=...)) and set_labels() uploads it without a pageable detour."""
+        if getattr(self, "_pin_labels", None) is None:
+            self._pin_labels = pinned_empty((self.n_window,), np.int32)
+        return self._pin_labels
 
     # ---- phase B
     def set_labels(self, labels_window):
@@ -189,6 +222,7 @@ class Region:
         if getattr(self, "_h", None):
             _lib.lib().phmrf_region_destroy(self._h)
             self._h = None
+        self._pin_unary = self._pin_w = self._pin_labels = None
 
     def __del__(self):
         try:
@@ -273,15 +307,19 @@ def log_multivariate_normal_density(X, means, covars, covariance_type='full', de
 
 
 def gco_cut_int(unary_i32, edge_ids, w_i32, V_i32, n_iter=-1, algorithm='expansion', init_labels=None,
-                return_energy=False):
-    """Host graph cut on already quantised arrays (include/phmrf_gco.h)."""
+                return_energy=False, out=None):
+    """Host graph cut on already quantised arrays (include/phmrf_gco.h).  `out`: int32 [n] buffer
+    the labels are written to (e.g. Region.label_staging())."""
     u = np.ascontiguousarray(unary_i32, dtype=np.int32)
     n, K = u.shape
     e = np.ascontiguousarray(edge_ids, dtype=np.int64).reshape(-1, 2)
     w = np.ascontiguousarray(w_i32, dtype=np.int32)
     V = np.ascontiguousarray(V_i32, dtype=np.int32)
     init = None if init_labels is None else np.ascontiguousarray(init_labels, dtype=np.int32)
-    out = np.empty(n, dtype=np.int32)
+    if out is None:
+        out = np.empty(n, dtype=np.int32)
+    elif out.dtype != np.int32 or out.shape != (n,) or not out.flags.c_contiguous:
+        raise ValueError("out must be a contiguous int32 array of %d labels" % n)
     en, en0 = C.c_longlong(), C.c_longlong()
     alg = {'swap': 0, 'expansion': 1}[algorithm]
     g = _lib.gco()
