@@ -14,6 +14,12 @@ namespace phmrf {
 
 static thread_local std::string g_error;
 static std::atomic<long long> g_launches{0};
+// One bulk transfer per direction and device at a time.  Regions driven from different threads
+// (the EM driver's pool, bench.py's end-to-end leg) would otherwise share the link in each
+// direction and advance in lock step -- every upload phase together, then every download phase
+// together -- and never use PCIe in both directions at once.  Taking turns pipelines them: one
+// region's integer cost arrays go down while the next one's features go up and its kernels run.
+static std::mutex g_h2d_turn[64], g_d2h_turn[64];
 
 void set_error(const std::string &msg) { g_error = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -81,7 +87,14 @@ struct phmrf_region {
     int64_t scratch_elems = 0;
     bool have_logp = false, have_unary = false, have_labels = false, have_rowmax = false;
     int64_t bytes = 0;
+    // small results (statistics, flags, dwf, counters) come back through a host-mapped buffer that a
+    // kernel writes (launch_publish), not through the copy engines
+    unsigned long long *h_small = nullptr;  // host view
+    unsigned long long *d_small = nullptr;  // device view of the same memory
 };
+
+// word offsets inside the mapped buffer
+enum { kSmFlag = 0, kSmBadLabel = 1, kSmDwf = 2 /* 2 words */, kSmAbsmax = 4 /* 2 words */, kSmStats = 8 };
 
 namespace {
 
@@ -114,6 +127,20 @@ bool cholesky_lower(const double *A, int d, double shift, std::vector<double> &L
         }
     }
     return true;
+}
+
+int alloc_small(phmrf_region *r) {
+    const size_t words = (size_t)kSmStats + (size_t)phmrf_stats_len(r->ctx);
+    void *h = nullptr, *d = nullptr;
+    PHMRF_CUDA(cudaHostAlloc(&h, words * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        cudaFreeHost(h);
+        return cuda_fail(e, "cudaHostGetDevicePointer", __FILE__, __LINE__);
+    }
+    r->h_small = static_cast<unsigned long long *>(h);
+    r->d_small = static_cast<unsigned long long *>(d);
+    return PHMRF_OK;
 }
 
 int ensure_scratch(phmrf_region *r, int64_t elems) {
@@ -361,6 +388,7 @@ int phmrf_region_create(phmrf_ctx *ctx, const double *X, int64_t n_own, int64_t 
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
     TRY(dev_alloc(r, &r->d_flags, 1));
     TRY(dev_alloc(r, &r->d_badlabel, 1));
+    TRY(alloc_small(r));
 
     // X: upload row-major, transpose on the device into the feature-major layout
     if (n_own > 0) {
@@ -492,6 +520,7 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
     TRY(dev_alloc(r, &r->d_stats, phmrf_stats_len(ctx)));
     TRY(dev_alloc(r, &r->d_flags, 1));
     TRY(dev_alloc(r, &r->d_badlabel, 1));
+    TRY(alloc_small(r));
     if (cudaMemsetAsync(r->d_X, 0, sizeof(double) * D * ld, r->stream) != cudaSuccess ||
         cudaMemsetAsync(r->d_rowmax, 0, sizeof(double) * ld, r->stream) != cudaSuccess ||
         launch_logp_init(r->d_logp, ld, K, r->stream) != PHMRF_OK) {
@@ -556,7 +585,11 @@ int phmrf_region_update_X(phmrf_region *r, const double *X) {
     if (r->n == 0) return PHMRF_OK;
     const int D = r->ctx->D;
     if ((rc = ensure_scratch(r, r->n * D)) != PHMRF_OK) return rc;
-    PHMRF_CUDA(cudaMemcpyAsync(r->d_scratch, X, sizeof(double) * r->n * D, cudaMemcpyHostToDevice, r->stream));
+    {
+        std::lock_guard<std::mutex> turn(g_h2d_turn[r->ctx->device]);
+        PHMRF_CUDA(cudaMemcpyAsync(r->d_scratch, X, sizeof(double) * r->n * D, cudaMemcpyHostToDevice, r->stream));
+        PHMRF_CUDA(cudaStreamSynchronize(r->stream));  // X may be reused by the caller; the turn ends with the copy
+    }
     if ((rc = launch_aos_to_soa(r->d_scratch, r->d_X, r->n, D, r->ld, r->stream)) != PHMRF_OK) return rc;
     r->have_logp = false;
     r->have_unary = false;
@@ -587,6 +620,7 @@ int phmrf_region_destroy(phmrf_region *r) {
     cudaFree(r->d_flags);
     cudaFree(r->d_badlabel);
     cudaFree(r->d_scratch);
+    if (r->h_small) cudaFreeHost(r->h_small);
     if (r->own_stream) cudaStreamDestroy(r->stream);
     cudaGetLastError();
     delete r;
@@ -638,10 +672,9 @@ int phmrf_emit_loglik(phmrf_region *r, double *absmax_out) {
     int rc = phmrf_emit_loglik_async(r);
     if (rc) return rc;
     if (absmax_out) {
-        unsigned long long bits = 0;
-        PHMRF_CUDA(cudaMemcpyAsync(&bits, r->d_absmax, sizeof(bits), cudaMemcpyDeviceToHost, r->stream));
+        if ((rc = launch_publish(r->d_small + kSmAbsmax, r->d_absmax, 1, false, r->stream)) != PHMRF_OK) return rc;
         PHMRF_CUDA(cudaStreamSynchronize(r->stream));
-        std::memcpy(absmax_out, &bits, sizeof(double));
+        std::memcpy(absmax_out, r->h_small + kSmAbsmax, sizeof(double));
     }
     return PHMRF_OK;
 }
@@ -692,16 +725,23 @@ int phmrf_quantise(phmrf_region *r, double dwf_in, double tol, int32_t *unary_i3
     if (rc) return rc;
     phmrf_ctx *ctx = r->ctx;
     const int K = ctx->K;
-    if (w_i32_out && r->E > 0)
-        PHMRF_CUDA(cudaMemcpyAsync(w_i32_out, r->d_edge_wi, sizeof(int32_t) * r->E, cudaMemcpyDeviceToHost, r->stream));
-    if (unary_i32_out && r->n > 0)
-        PHMRF_CUDA(cudaMemcpyAsync(unary_i32_out, r->d_unary, sizeof(int32_t) * r->n * K, cudaMemcpyDeviceToHost,
-                                   r->stream));
     double dwf2[2] = {0, 0};
     unsigned long long nb = 0;
-    PHMRF_CUDA(cudaMemcpyAsync(dwf2, r->d_dwf, sizeof(dwf2), cudaMemcpyDeviceToHost, r->stream));
-    PHMRF_CUDA(cudaMemcpyAsync(&nb, r->d_absmax + 1, sizeof(nb), cudaMemcpyDeviceToHost, r->stream));
+    if ((w_i32_out && r->E > 0) || (unary_i32_out && r->n > 0)) {
+        PHMRF_CUDA(cudaStreamSynchronize(r->stream));  // the kernels first: a turn is spent on copying only
+        std::lock_guard<std::mutex> turn(g_d2h_turn[ctx->device]);
+        if (w_i32_out && r->E > 0)
+            PHMRF_CUDA(cudaMemcpyAsync(w_i32_out, r->d_edge_wi, sizeof(int32_t) * r->E, cudaMemcpyDeviceToHost, r->stream));
+        if (unary_i32_out && r->n > 0)
+            PHMRF_CUDA(cudaMemcpyAsync(unary_i32_out, r->d_unary, sizeof(int32_t) * r->n * K, cudaMemcpyDeviceToHost,
+                                       r->stream));
+        PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+    }
+    if ((rc = launch_publish(r->d_small + kSmDwf, r->d_dwf, 2, false, r->stream)) != PHMRF_OK) return rc;
+    if ((rc = launch_publish(r->d_small + kSmAbsmax, r->d_absmax, 2, false, r->stream)) != PHMRF_OK) return rc;
     PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+    std::memcpy(dwf2, r->h_small + kSmDwf, sizeof(dwf2));
+    nb = r->h_small[kSmAbsmax + 1];
     if (dwf_out) *dwf_out = dwf2[0];
     if (n_boundary) *n_boundary = (int64_t)nb;
     if (boundary_idx && boundary_cap > 0 && nb > 0) {
@@ -724,8 +764,9 @@ int phmrf_set_labels(phmrf_region *r, const int32_t *labels_window) {
     // range check on the device (a host loop over 4e7 labels costs more than the copy)
     long long first_bad = -1;
     if ((rc = launch_check_labels(r->d_labels, r->n_window, r->ctx->K, r->d_badlabel, r->stream)) != PHMRF_OK) return rc;
-    PHMRF_CUDA(cudaMemcpyAsync(&first_bad, r->d_badlabel, sizeof(long long), cudaMemcpyDeviceToHost, r->stream));
+    if ((rc = launch_publish(r->d_small + kSmBadLabel, r->d_badlabel, 1, false, r->stream)) != PHMRF_OK) return rc;
     PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+    first_bad = (long long)r->h_small[kSmBadLabel];
     if (first_bad >= 0) {
         r->have_labels = false;
         set_error("phmrf_set_labels: label out of range at node " + std::to_string(first_bad));
@@ -857,9 +898,11 @@ int phmrf_estep_stats(phmrf_region *r, int estimate_type, double *post_out, doub
             if ((rc = launch_soa_to_aos(r->d_scratch, aos, r->n, K, r->ld, r->stream)) != PHMRF_OK) return rc;
             PHMRF_CUDA(cudaMemcpyAsync(post_out, aos, sizeof(double) * r->n * K, cudaMemcpyDeviceToHost, r->stream));
         }
-        PHMRF_CUDA(cudaMemcpyAsync(host.data(), r->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, r->stream));
-        PHMRF_CUDA(cudaMemcpyAsync(&flag, r->d_flags, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+        if ((rc = launch_publish(r->d_small + kSmStats, r->d_stats, (int)len, false, r->stream)) != PHMRF_OK) return rc;
+        if ((rc = launch_publish(r->d_small + kSmFlag, r->d_flags, 1, true, r->stream)) != PHMRF_OK) return rc;
         PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+        std::memcpy(host.data(), r->h_small + kSmStats, sizeof(double) * len);
+        flag = (int)(long long)r->h_small[kSmFlag];
         if (!(flag & 1) || attempt == 1) break;
         // the pipeline kernel met a soft-max overflow (only reachable with extreme beta):
         // redo the region on the general kernel, which uses the exact maximum

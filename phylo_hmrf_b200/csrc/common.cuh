@@ -60,6 +60,11 @@ int launch_rowmax(const double *logp, int64_t n, int K, double *rowmax, unsigned
                   cudaStream_t s);
 int launch_check_labels(const int32_t *labels, int64_t n, int K, long long *first_bad, cudaStream_t s);
 int launch_fill(double *p, double v, int64_t count, cudaStream_t s);
+// Small results to the host without the copy engines: the kernel stores `count` 64-bit words (or,
+// with src32, sign-extended 32-bit words) into a host-mapped pinned buffer.  A DMA read-back of a few
+// bytes queues behind whatever bulk download another region has in flight (tens of milliseconds);
+// stores from an SM do not.
+int launch_publish(unsigned long long *dst_mapped, const void *src, int count, bool src32, cudaStream_t s);
 // rows of the log-likelihood matrix: K rounded up to the 8-state tiles of the pipeline kernel;
 // the padding rows hold kLogpPad for the lifetime of a region
 __host__ __device__ inline int logp_rows(int K) { return (K + 7) / 8 * 8; }

@@ -299,6 +299,22 @@ __global__ void dwf_kernel(const unsigned long long *absmax_bits, double wmax, d
     dwf_dev[1] = __longlong_as_double((long long)absmax_bits[0]);
 }
 
+__global__ void publish_kernel(unsigned long long *__restrict__ dst, const void *__restrict__ src, int count, bool src32) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        dst[i] = src32 ? (unsigned long long)(long long)reinterpret_cast<const int *>(src)[i]
+                       : reinterpret_cast<const unsigned long long *>(src)[i];
+    __threadfence_system();
+}
+
+int launch_publish(unsigned long long *dst_mapped, const void *src, int count, bool src32, cudaStream_t s) {
+    if (count <= 0) return PHMRF_OK;
+    const int blocks = (count + 255) / 256;
+    publish_kernel<<<blocks < 32 ? blocks : 32, 256, 0, s>>>(dst_mapped, src, count, src32);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
 int launch_fill(double *p, double v, int64_t count, cudaStream_t s) {
     if (count <= 0) return PHMRF_OK;
     const int64_t blocks = (count + 255) / 256;

@@ -14,6 +14,18 @@ from __future__ import annotations
 import numpy as np
 
 
+# hg38 autosome lengths (chr1..chr22; the public assembly constants the reference reads from
+# example_input/hg38.chrom.sizes): BASELINE config 4 is one diagonal region per autosome at 50 kb
+HG38_AUTOSOME_BP = (248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+                    133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+                    58617616, 64444167, 46709983, 50818468)
+
+
+def autosome_bins(resolution=50000):
+    """Bins per autosome with the reference's floor division (utility.py:2516)."""
+    return [bp // resolution for bp in HG38_AUTOSOME_BP]
+
+
 def tri_row_start(B, x):
     """Index of node (x, x) in the row-major upper triangle of a B-bin region."""
     x = np.asarray(x, dtype=np.int64)
