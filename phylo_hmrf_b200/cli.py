@@ -62,10 +62,29 @@ def _load_raw(opts, data_path, resolution, device):
                                         device=device)
 
 
+def _launch_context(device):
+    """(device, rank, world, comm or None).  Under `torchrun` (RANK/LOCAL_RANK/WORLD_SIZE in the
+    environment) one process per GPU: the device is LOCAL_RANK, the process binds to the cores next
+    to that GPU and joins the NCCL group; files are written by rank 0 only."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return device, 0, 1, None
+    import torch
+    import torch.distributed as td
+    from . import dist as pdist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pdist.bind_to_gpu_numa(local)
+    torch.cuda.set_device(local)
+    if not td.is_initialized():
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return local, td.get_rank(), world, td
+
+
 def run(opts, device=0):
     """phylo_hmrf.py:1570-1749.  Returns the dict written to the `.mat` file."""
     import scipy.io
     from .hmrf import phyloHMRF
+    device, rank, world, td = _launch_context(device)
     run_id, K = int(opts.run_id), int(opts.num_states)
     cons_param = float(opts.cons_param)
     resolution = int(opts.resolution)
@@ -81,14 +100,21 @@ def run(opts, device=0):
         edge_list_vec = list(np.load(f2, allow_pickle=True))
         len_vec = np.atleast_2d(np.loadtxt(f3, dtype='int32', delimiter='\t')).tolist()
     else:   # phylo_hmrf.py:1630-1706: align the species' contact files, build the regions, write the caches
-        samples, len_vec, edge_list_vec = _load_raw(opts, data_path, resolution, device)
-        os.makedirs(output_path, exist_ok=True)
-        np.save(f1, samples)
-        ev = np.empty(len(edge_list_vec), dtype=object)
-        for i, e in enumerate(edge_list_vec):
-            ev[i] = e
-        np.save(f2, ev, allow_pickle=True)
-        np.savetxt(f3, np.asarray(len_vec), fmt='%d', delimiter='\t')
+        if rank == 0:
+            samples, len_vec, edge_list_vec = _load_raw(opts, data_path, resolution, device)
+            os.makedirs(output_path, exist_ok=True)
+            np.save(f1, samples)
+            ev = np.empty(len(edge_list_vec), dtype=object)
+            for i, e in enumerate(edge_list_vec):
+                ev[i] = e
+            np.save(f2, ev, allow_pickle=True)
+            np.savetxt(f3, np.asarray(len_vec), fmt='%d', delimiter='\t')
+        if world > 1:       # the other ranks read what rank 0 prepared
+            td.barrier()
+            if rank != 0:
+                samples = np.load(f1)
+                edge_list_vec = list(np.load(f2, allow_pickle=True))
+                len_vec = np.atleast_2d(np.loadtxt(f3, dtype='int32', delimiter='\t')).tolist()
     if int(opts.method_mode) != 1:
         raise SystemExit("method_mode 1 (Phylo-HMRF) is the only mode of the reference's run()")
     model = phyloHMRF(n_components=K, run_id=run_id, n_samples=samples.shape[0], n_features=samples.shape[-1],
@@ -103,8 +129,9 @@ def run(opts, device=0):
     params_vec1, params_vec2, params_vecList, iter_id1, iter_id2, cost_vec, state_vec = res
     mdict = {'state_vec': state_vec, 'len_vec': np.asarray(len_vec), 'params_vec1': params_vec1,
              'params_vec2': params_vec2, 'iter_id1': iter_id1, 'iter_id2': iter_id2, 'cost_vec': cost_vec}
-    os.makedirs(output_path, exist_ok=True)
-    scipy.io.savemat("%s/estimate_ou_%d_%.2f_%d.mat" % (output_path, run_id, cons_param, K), mdict)
+    if rank == 0:
+        os.makedirs(output_path, exist_ok=True)
+        scipy.io.savemat("%s/estimate_ou_%d_%.2f_%d.mat" % (output_path, run_id, cons_param, K), mdict)
     model.close()
     return mdict
 

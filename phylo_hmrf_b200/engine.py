@@ -83,6 +83,7 @@ class Model:
 
 class Region:
     """One region (or row band) resident on the device; see phmrf_region_create."""
+    has_logp = False     # a log-likelihood is on the device (emitted or uploaded)
 
     def __init__(self, model, X, edge_ids, edge_w, n_window=None, own_offset=0, stream=None):
         X = as_f64(X)
@@ -114,8 +115,10 @@ class Region:
         if want_absmax:
             v = C.c_double()
             check(_lib.lib().phmrf_emit_loglik(self._h, C.byref(v)))
+            self.has_logp = True
             return v.value
         check(_lib.lib().phmrf_emit_loglik(self._h, None))
+        self.has_logp = True
         return None
 
     def logprob(self):
@@ -128,6 +131,7 @@ class Region:
         if lp.shape != (self.n, self.model.K):
             raise ValueError("logprob must be [%d, %d]" % (self.n, self.model.K))
         check(_lib.lib().phmrf_set_logprob(self._h, dptr(lp)))
+        self.has_logp = True
 
     def pairwise_potential(self, estimate_type):
         out = np.empty((self.n, self.model.K), dtype=np.float64)
@@ -193,6 +197,7 @@ class Region:
     # ---- enqueue-only (bench)
     def emit_loglik_async(self):
         check(_lib.lib().phmrf_emit_loglik_async(self._h))
+        self.has_logp = True
 
     def quantise_async(self, dwf=0.0, tol=1e-9):
         check(_lib.lib().phmrf_quantise_async(self._h, float(dwf), float(tol)))

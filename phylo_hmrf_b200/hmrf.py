@@ -76,7 +76,6 @@ class phyloHMRF(object):
         self._model = engine.Model(self.n_components, self.n_features, device)
         self._regions = []
         self._model_key = None
-        self._last_logprob = {}
 
         self.initial_mode, self.initial_w1, self.initial_w1a, self.initial_w2 = (
             initial_mode, initial_weight, initial_weight1, initial_magnitude)
@@ -102,12 +101,28 @@ class phyloHMRF(object):
             self._model.set_model(self.means_, self._covars_, self.edge_potential)
             self._model_key = key
 
-    def _region_for(self, X, edge_ids, edge_w):
-        """The resident region whose inputs are these very arrays, else a temporary one."""
+    @staticmethod
+    def _where(a):
+        """(address, shape, strides) of an array: two views with the same triple are the same memory."""
+        a = np.asarray(a)
+        return (a.__array_interface__['data'][0], a.shape, a.strides)
+
+    def _region_for(self, X, edge_ids, edge_w, n=None):
+        """The resident region built from these very edge arrays, else a temporary one.  A resident
+        region computes from the features it was built from; when the caller passes other data
+        (the reference uses the X it is given, phylo_hmrf.py:470-507) that data is uploaded first.
+        X=None (with the node count n): the features play no part in what the caller computes."""
+        n = len(X) if X is not None else int(n)
         for r, reg in enumerate(self._regions):
-            if edge_ids is self.edge_idList_undirected_vec[r] and len(X) == reg.n:
+            if reg is not None and edge_ids is self.edge_idList_undirected_vec[r] and n == reg.n:
+                if X is not None and self._where(X) != reg._x_where:
+                    reg.update_X(np.asarray(X))
+                    reg._x_where = self._where(X)
+                    reg._host_logprob = None
                 return reg, False
-        return self._model.region(X, edge_ids, edge_w), True
+        reg = self._model.region(X if X is not None else np.zeros((n, self.n_features)), edge_ids, edge_w)
+        reg._host_logprob = None
+        return reg, True
 
     # ------------------------------------------------------------------ constants
     def _pairwise_potential(self):
@@ -127,8 +142,14 @@ class phyloHMRF(object):
         num_region = len(len_vec)
         w_vec, id_vec, inc_vec = [None] * num_region, [None] * num_region, [None] * num_region
         for reg in self._regions:
-            reg.close()
+            if reg is not None:
+                reg.close()
         self._regions = []
+        # under torchrun a rank keeps resident only the whole regions the plan gives it (row bands of
+        # larger regions are made resident by the EM driver, _prepare_bands)
+        from . import dist as _pdist, em as _em
+        world, rank = _pdist.world_info()
+        owned = set(_em.make_plan(len_vec, world)[0][rank]) if world > 1 else set(range(num_region))
         for r in range(num_region):
             n_samples, s1, s2 = int(len_vec[r][0]), int(len_vec[r][1]), int(len_vec[r][2])
             edge_list = np.asarray(edge_list_vec[r], dtype=np.float64)
@@ -136,13 +157,26 @@ class phyloHMRF(object):
             ids = np.int64(edge_list[:, 0:2])
             w_vec[r], id_vec[r] = w, ids
             inc_vec[r] = self._connected_edge(ids, n_samples)
-            self._regions.append(self._model.region(np.asarray(X)[s1:s2], ids, w))
+            if r not in owned:
+                self._regions.append(None)
+                continue
+            reg = self._model.region(np.asarray(X)[s1:s2], ids, w)
+            reg._x_where = self._where(np.asarray(X)[s1:s2])
+            reg._host_logprob = None       # the host array the device log-likelihood currently equals
+            self._regions.append(reg)
         return w_vec, id_vec, inc_vec
 
     # ------------------------------------------------------------------ phase A
     def _compute_log_likelihood(self, X):
-        """phylo_hmrf.py:266-268 (sklearn 0.18 'full' density) on the device."""
+        """phylo_hmrf.py:266-268 (sklearn 0.18 'full' density) on the device.  X that is the very slice a
+        resident region was built from is not uploaded again."""
         self._sync_model()
+        where = self._where(X)
+        for reg in self._regions:
+            if reg is not None and where == reg._x_where:
+                reg.emit_loglik()
+                reg._host_logprob = reg.logprob()
+                return reg._host_logprob
         reg = self._model.region(X, np.zeros((0, 2), dtype=np.int64), np.zeros(0))
         try:
             reg.emit_loglik()
@@ -151,21 +185,25 @@ class phyloHMRF(object):
             reg.close()
 
     def _estimate_state_graphcuts_gco(self, X, init_labels1, edge_idList_undirected, edge_weightList_undirected,
-                                      want_logprob=True):
+                                      want_logprob=True, staged_labels=False):
         """phylo_hmrf.py:486-507: emission, integer cost arrays (GPU), alpha-beta swap with
         5000 cycles from ``init_labels1`` (host GCO).  Returns (labels, logprob)."""
         self._sync_model()
         reg, temp = self._region_for(X, edge_idList_undirected, edge_weightList_undirected)
         try:
             reg.emit_loglik()
-            q = reg.quantise()
+            # resident regions keep page-locked staging buffers: the integer arrays go straight from the
+            # device into the graph cut, and its labels straight back (no pageable copies in between)
+            q = reg.quantise(staged=not temp)
             max_cycles1 = 5000
             labels = engine.gco_cut_int(q["unary_i32"], edge_idList_undirected, q["w_i32"], q["V_i32"],
-                                        n_iter=max_cycles1, algorithm='swap', init_labels=init_labels1)
+                                        n_iter=max_cycles1, algorithm='swap', init_labels=init_labels1,
+                                        out=None if temp else reg.label_staging())
             self.last_quantise = q
             logprob = reg.logprob() if want_logprob else None
-            if not temp:
-                self._last_logprob[id(reg)] = logprob
+            reg._host_logprob = logprob
+            if not temp and not staged_labels:
+                labels = labels.copy()     # the staging buffer is overwritten by the region's next graph cut
             return labels, logprob
         finally:
             if temp:
@@ -183,21 +221,20 @@ class phyloHMRF(object):
 
     # ------------------------------------------------------------------ phase B
     def _prepare_phase_b(self, reg, label, logprob):
-        if logprob is not None and logprob is not self._last_logprob.get(id(reg)):
+        if logprob is not None and logprob is not reg._host_logprob:
             reg.set_logprob(logprob)
-            self._last_logprob[id(reg)] = logprob
+            reg._host_logprob = logprob
         reg.set_labels(np.asarray(label))
 
     def _pairwise_compare(self, label, neighbor_edgeIdx, edge_weightList, edge_idList):
         """phylo_hmrf.py:398-410 -> pp [N,K]."""
         self._sync_model()
         n = len(label)
-        reg, temp = self._region_for(np.zeros((n, self.n_features)), edge_idList, edge_weightList)
+        reg, temp = self._region_for(None, edge_idList, edge_weightList, n=n)
         try:
-            if id(reg) not in self._last_logprob:
-                reg.set_logprob(np.zeros((n, self.n_components)))
-                if not temp:
-                    self._last_logprob[id(reg)] = None
+            if not reg.has_logp:
+                reg.set_logprob(np.zeros((n, self.n_components)))   # the potential does not depend on it
+                reg._host_logprob = None
             reg.set_labels(np.asarray(label))
             return reg.pairwise_potential(self.estimate_type)
         finally:
@@ -220,11 +257,10 @@ class phyloHMRF(object):
         ``pairwise_prob_normalize`` is recomputed on the device from (label, edges): it is a
         function of exactly those inputs at the reference's only call site (:352)."""
         self._sync_model()
-        reg, temp = self._region_for(X, edge_idList, edge_weightList)
+        reg, temp = self._region_for(None, edge_idList, edge_weightList, n=len(label))   # the costs do not read X
         try:
             reg.set_logprob(logprob1)
-            if not temp:
-                self._last_logprob[id(reg)] = logprob1
+            reg._host_logprob = logprob1
             reg.set_labels(np.asarray(label))
             _, sums, _ = reg.estep_stats(self.estimate_type)
             return engine.costs_from_sums(sums, reg.n)
@@ -249,7 +285,7 @@ class phyloHMRF(object):
         init_labels = self.labels_local[s1:s2].copy()
         labels, _ = self._estimate_state_graphcuts_gco(
             X[s1:s2], init_labels, self.edge_idList_undirected_vec[region_id],
-            self.edge_weightList_undirected_vec[region_id], want_logprob=False)
+            self.edge_weightList_undirected_vec[region_id], want_logprob=False, staged_labels=True)
         reg.set_labels(labels)
         stats, sums, _ = reg.estep_stats(self.estimate_type)
         c = engine.costs_from_sums(sums, reg.n)
@@ -304,108 +340,119 @@ class phyloHMRF(object):
             self.finalize_fn(self, params_vec)
 
     def fit_accumulate_test(self, X, len_vec, threshold, annotation, m_iter, lengths=None, n_threads=None):
-        """base.py:301-455, without fork.  Same iteration, cost aggregation (N_r/N weights,
-        :332-337, :384-396), convergence tests (:402-435) and best-iteration bookkeeping;
-        regions run through `_predict_posteriors` on a thread pool (the GPU kernels and the
-        host graph cut release the GIL), results are gathered from a queue exactly as the
-        parent process does.  Returns (params_vec, params_vec1, params_vecList, iter_id1,
-        iter_id2, cost_vec, t_labels)."""
-        try:
-            import queue as _queue
-        except ImportError:  # py2
-            import Queue as _queue
-        from concurrent.futures import ThreadPoolExecutor
+        """base.py:301-455 without fork: see `phylo_hmrf_b200.em` (iteration, cost aggregation with the
+        N_r/N weights, convergence tests, best-iteration bookkeeping; regions on a thread pool; under
+        `torchrun` the regions -- or the row bands of a region too large for one GPU -- are spread over
+        the ranks).  Returns (params_vec, params_vec1, params_vecList, iter_id1, iter_id2, cost_vec,
+        t_labels)."""
+        from . import em
+        return em.run(self, X, len_vec, threshold, annotation, m_iter, lengths=lengths, n_threads=n_threads)
 
-        self._init(X, lengths=lengths)
-        self._check()
-        max_iter = m_iter
-        max_iter1 = 50  # iterations after the previous minimum
-        pairwise_cost_pre, unary_cost_pre, cost1_pre = 0.001, 0.001, 0.001
-        threshold1, threshold2 = threshold, threshold
-        cost_vec = []
-        min_cost = [0, 1000]
-        min_cost1 = [0, 1000]
-        params_vec = self.params_vec1.copy()
-        params_vec1 = self.params_vec1.copy()
-        num_region = len(len_vec)
-        ratio_vec = np.zeros(num_region)
-        for i in range(0, num_region):
-            ratio_vec[i] = len_vec[i][0]
-        n_samples = int(sum(ratio_vec))
-        ratio_vec = ratio_vec * 1.0 / n_samples
-        params_vecList = []
-        t_labels = np.zeros(n_samples)
-        workers = n_threads or min(num_region, 8)
-        # one process per GPU (torchrun): whole regions are dealt to the ranks by node count, every rank
-        # gathers all result tuples and then runs the same (deterministic) aggregation and M-step
-        from . import dist as _pdist
-        world, rank = _pdist.world_info()
-        if world > 1:
-            owner = _pdist.assign_regions([lv[0] for lv in len_vec], world)
-            my_regions = [r for r in range(num_region) if owner[r] == rank]
-        else:
-            my_regions = list(range(num_region))
+    # ------------------------------------------------------------------ row bands (SURVEY 8(e))
+    def _prepare_bands(self, X, len_vec, banded, comm):
+        """Make this rank's row bands resident: for each band the owned rows' features and the edges
+        incident to them (ids local to the band's label window).  The rank that owns a banded region's
+        graph cut also keeps an edge-only region for the integer edge weights of the whole region."""
+        from . import em
+        self._bands = {}
+        self._edge_regions = {}
+        X = np.asarray(X)
+        for rid, plist in banded.items():
+            lv = len_vec[rid]
+            s1 = int(lv[1])
+            kind, n1, n2 = em._geometry(lv)
+            ids, w = self.edge_idList_undirected_vec[rid], self.edge_weightList_undirected_vec[rid]
+            for bi, (rank, row0, row1) in enumerate(plist):
+                if rank != comm.rank:
+                    continue
+                own0, own1, win0, win1 = em.band_window(kind, n1, n2, row0, row1)
+                a, b = ids[:, 0], ids[:, 1]
+                keep = ((a >= own0) & (a < own1)) | ((b >= own0) & (b < own1))
+                reg = self._model.region(X[s1 + own0:s1 + own1], ids[keep] - win0, w[keep], n_window=win1 - win0,
+                                         own_offset=own0 - win0)
+                # every band quantises against the REGION's largest edge weight (pygco's down-weight factor)
+                reg.set_weight_max(float(np.max(np.abs(w))) if len(w) else 0.0)
+                self._bands[(rid, bi)] = (reg, own0, own1, win0, win1)
+            if plist[0][0] == comm.rank:
+                self._edge_regions[rid] = self._model.region(np.zeros((0, self.n_features)), ids, w,
+                                                             n_window=int(lv[0]), own_offset=0)
 
-        for iter in range(max_iter):
-            stats = self._initialize_sufficient_statistics()
-            self._sync_model()
-            self.queue = _queue.Queue()
-            if workers > 1 and len(my_regions) > 1:
-                with ThreadPoolExecutor(max_workers=workers) as pool:
-                    list(pool.map(lambda r: self._predict_posteriors(X, len_vec, r, self.queue), my_regions))
-            else:
-                for region_id in my_regions:
-                    self._predict_posteriors(X, len_vec, region_id, self.queue)
-            results = [self.queue.get() for _ in range(len(my_regions))]
-            if world > 1:
-                results = _pdist.all_gather_results(results)
+    def _band_emit(self, rid, bi):
+        """Emission of one band -> its max|logp|."""
+        return self._bands[(rid, bi)][0].emit_loglik(want_absmax=True)
 
-            pairwise_cost1, pairwise_cost, unary_cost, cost1 = 0, 0, 0, 0
-            id1 = 3
-            labels = np.zeros(n_samples)
-            # fixed (region id) order so that the floating-point sums do not depend on thread timing
-            for vec1 in sorted(results, key=lambda v: v[0]):
-                region_id = vec1[0]
-                pairwise_cost1 += vec1[id1] * ratio_vec[region_id]
-                pairwise_cost += vec1[id1 + 1] * ratio_vec[region_id]
-                unary_cost += vec1[id1 + 2] * ratio_vec[region_id]
-                cost1 += vec1[id1 + 3] * ratio_vec[region_id]
-                s1, s2 = len_vec[region_id][1], len_vec[region_id][2]
-                stats = self._accumulate_sufficient_statistics_1(stats, vec1[1])
-                labels[s1:s2] = vec1[2]
+    def _band_quantise(self, rid, bi, dwf):
+        """Integer unary [n_band, K] of one band under the region-wide down-weight factor."""
+        return self._bands[(rid, bi)][0].quantise(dwf=dwf, want_edges=False, staged=True)["unary_i32"]
 
-            t_difference1 = abs((pairwise_cost - pairwise_cost_pre) * 1.0 / pairwise_cost_pre)
-            t_difference2 = abs((unary_cost - unary_cost_pre) * 1.0 / unary_cost_pre)
-            t_difference3 = abs((cost1 - cost1_pre) * 1.0 / cost1_pre)
-            pairwise_cost_pre, unary_cost_pre, cost1_pre = pairwise_cost, unary_cost, cost1
-            cost_vec.append([iter, pairwise_cost, unary_cost, cost1])
-            params_vecList.append(self.params_vec1.copy())
-            self.labels = labels.copy()
+    def _region_edge_costs(self, rid, dwf):
+        """(w_i32 [E], V_i32 [K,K]) of a whole banded region, on the rank that runs its graph cut."""
+        reg = self._edge_regions[rid]
+        reg.emit_loglik()
+        q = reg.quantise(dwf=dwf, want_unary=False, staged=True)
+        return q["w_i32"], q["V_i32"]
 
-            if cost1 < min_cost[1]:
-                min_cost = [iter, cost1]
-                params_vec = self.params_vec1.copy()
-                self.labels_local = self.labels.copy()  # current local optimal state estimate
-            if cost1 < min_cost1[1] and iter >= 3:
-                min_cost1 = [iter, cost1]
-                params_vec1 = self.params_vec1.copy()
-                t_labels = self.labels.copy()  # keep the estimated labels
-            if ((t_difference1 < threshold1 and t_difference2 < threshold2) or (t_difference3 < threshold1)) and (iter > 5):
-                break
-            if iter > max_iter:
-                break
-            if iter - min_cost1[0] > max_iter1:
-                break
-            self._do_mstep(stats)
+    def _band_estep(self, rid, bi, labels_window):
+        """E-step of one band -> (statistics flattened post|obs|obs*obs.T, the three cost sums)."""
+        reg = self._bands[(rid, bi)][0]
+        reg.set_labels(labels_window)
+        stats, sums, _ = reg.estep_stats(self.estimate_type)
+        return np.concatenate([stats['post'].ravel(), stats['obs'].ravel(), stats['obs*obs.T'].ravel()]), sums
 
-        self.params_vec1 = params_vec1.copy()
-        self._ou_param_varied_constraint(params_vec)
-        cost_vec = np.asarray(cost_vec)
-        params_vecList = np.asarray(params_vecList)
-        return params_vec, params_vec1, params_vecList, min_cost[0], min_cost1[0], cost_vec, t_labels
+    def _banded_region(self, rid, len_vec, plist, comm):
+        """One EM iteration of a region whose rows are spread over several ranks (called by every rank).
+        -> (this rank's share of [statistics | 3 cost sums], the region's labels on the rank that ran
+        the graph cut, else None)."""
+        from . import em
+        lv = len_vec[rid]
+        n_region, s1, s2 = int(lv[0]), int(lv[1]), int(lv[2])
+        kind, n1, n2 = em._geometry(lv)
+        K = self.n_components
+        owner = plist[0][0]
+        mine = [bi for bi, (rank, _, _) in enumerate(plist) if rank == comm.rank]
+        # emission; the region's max|logp| decides the down-weight factor every band must share
+        absmax = comm.max(np.array([max([self._band_emit(rid, bi) for bi in mine] + [0.0])]))[0]
+        w = self.edge_weightList_undirected_vec[rid]
+        wv = (float(np.max(np.abs(w))) if len(w) else 0.0) * float(np.max(self.edge_potential))
+        dwf = (wv if wv > absmax else absmax) + 1e-10          # pygco: max(max|unary|, max|w|*max V) + 1e-10
+        # integer unary of every band to the owner of the graph cut
+        unary = np.empty((n_region, K), dtype=np.int32) if comm.rank == owner else None
+        for bi, (rank, row0, row1) in enumerate(plist):
+            own0, own1, _, _ = em.band_window(kind, n1, n2, row0, row1)
+            if rank == comm.rank:
+                u = self._band_quantise(rid, bi, dwf)
+                if comm.rank == owner:
+                    unary[own0:own1] = u
+                else:
+                    comm.send(u, owner)
+            elif comm.rank == owner:
+                unary[own0:own1] = comm.recv((own1 - own0, K), np.int32, rank)
+        labels = None
+        if comm.rank == owner:
+            w_i32, V_i32 = self._region_edge_costs(rid, dwf)
+            labels = engine.gco_cut_int(unary, self.edge_idList_undirected_vec[rid], w_i32, V_i32, n_iter=5000,
+                                        algorithm='swap', init_labels=self.labels_local[s1:s2].copy())
+        # label windows back to the bands, E-step per band
+        n_stat = K * (1 + self.n_features + self.n_features * self.n_features)
+        part = np.zeros(n_stat + 3)
+        for bi, (rank, row0, row1) in enumerate(plist):
+            _, _, win0, win1 = em.band_window(kind, n1, n2, row0, row1)
+            if rank == comm.rank:
+                lw = labels[win0:win1] if comm.rank == owner else comm.recv((win1 - win0,), np.int32, owner)
+                flat, sums = self._band_estep(rid, bi, np.ascontiguousarray(lw, dtype=np.int32))
+                part[:n_stat] += flat
+                part[n_stat:] += sums
+            elif comm.rank == owner:
+                comm.send(np.ascontiguousarray(labels[win0:win1], dtype=np.int32), rank)
+        return part, labels
 
     def close(self):
         for reg in self._regions:
+            if reg is not None:
+                reg.close()
+        for entry in getattr(self, "_bands", {}).values():
+            entry[0].close()
+        for reg in getattr(self, "_edge_regions", {}).values():
             reg.close()
-        self._regions = []
+        self._regions, self._bands, self._edge_regions = [], {}, {}
         self._model.close()

@@ -18,16 +18,13 @@ from phylo_hmrf_b200 import dist as pdist
 B, D, K, ET, SEED = 40, 4, 6, 3, 31
 
 
-def _band_oracle(g, means, covars, V, labels_window, dwf=None):
-    """What one rank computes for its band (oracle stand-in for the kernels)."""
+def _band_oracle(g, means, covars, V, labels_window, dwf=None, et=ET):
+    """What one rank computes for its band (oracle stand-in for the kernels): the window-sized label
+    array lets the vectorised oracle see the halo labels; only the owned rows enter the sums."""
     o0, n = g["own_offset"], g["n_own"]
     X = g["X_own"]
     lp = orc.compute_log_likelihood(X, means, covars)
-    # window-sized arrays so that the vectorised oracle sees the halo labels; rows outside the
-    # band are zero-filled and excluded from the sums below
-    lp_win = np.zeros((g["n_window"], K))
-    lp_win[o0:o0 + n] = lp
-    pp = orc.pairwise_compare_vec(V, labels_window, g["edge_w"], g["edge_ids"], ET)[o0:o0 + n]
+    pp = orc.pairwise_compare_vec(V, labels_window, g["edge_w"], g["edge_ids"], et)[o0:o0 + n]
     lab = labels_window[o0:o0 + n]
     post = orc._stable_softmax(lp - pp)
     pwn = orc._stable_softmax(-pp)
