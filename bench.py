@@ -198,6 +198,8 @@ def run_ours(args):
     cores = pdist.bind_to_gpu_numa(local_rank)   # before any pinned allocation
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = workloads()[args.workload]
     d, K, bins, n_bands = wl["d"], wl["K"], wl["regions"], wl["bands"]
