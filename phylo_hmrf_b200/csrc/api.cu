@@ -848,12 +848,7 @@ static int estep_enqueue(phmrf_region *r, int estimate_type, bool want_post, boo
     if (ctx->potts && !force_general && !want_pp && r->W > 0 && std::fabs(a.s_bound) < 100.0) {
         // per-slot factors of the pipeline kernel: constant while beta and the weights are
         const int weighted = estimate_type == 3 ? 1 : 0;
-        // PHMRF_GRID_IMPLICIT=0 keeps grid-built regions on the explicit neighbour slots (A/B timing)
-        static const bool implicit_ok = [] {
-            const char *v = getenv("PHMRF_GRID_IMPLICIT");
-            return !(v != nullptr && v[0] == '0');
-        }();
-        if (r->d_fwd && implicit_ok) {
+        if (r->d_fwd) {
             // region built from the grid geometry: implicit neighbours, each weight stored once
             if (r->fwd_weighted != weighted || r->fwd_beta != ctx->beta) {
                 if ((rc = launch_fwd_factor(r->d_fwd, 4 * r->ldw, ctx->beta, weighted, r->stream)) != PHMRF_OK) return rc;

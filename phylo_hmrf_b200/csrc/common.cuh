@@ -65,8 +65,11 @@ int launch_fill(double *p, double v, int64_t count, cudaStream_t s);
 // bytes queues behind whatever bulk download another region has in flight (tens of milliseconds);
 // stores from an SM do not.
 int launch_publish(unsigned long long *dst_mapped, const void *src, int count, bool src32, cudaStream_t s);
-// rows of the log-likelihood matrix: K rounded up to the 8-state tiles of the pipeline kernel;
-// the padding rows hold kLogpPad for the lifetime of a region
+// rows of the log-likelihood matrix: K rounded up to the 8-state tiles of the pipeline kernel.  The
+// padding rows keep their values for the lifetime of a region: row K of an odd K holds kLogpPad (the
+// pipeline evaluates states in pairs: exp(-1e6 - shift) is a zero weight), the rows from the next even
+// number on hold 0.0 -- the pipeline never evaluates them, and the bulk copy then drops a zero WEIGHT
+// for them straight into the soft-max buffer the statistics product reads.
 __host__ __device__ inline int logp_rows(int K) { return (K + 7) / 8 * 8; }
 constexpr double kLogpPad = -1.0e6;
 int launch_logp_init(double *logp, int64_t ld, int K, cudaStream_t s);
@@ -112,13 +115,12 @@ struct EstepArgs {
     int64_t grid_n2, grid_rows;
     int64_t own_start_gid;    // region-global node id of the first owned node
 };
-// g[s][i] = exp(beta * (weighted ? w[s][i] : 1)) for occupied slots, 1 otherwise (kernels_b2.cu)
+// g[s][i] = exp(beta * (weighted ? w[s][i] : 1)) for occupied slots, 1 otherwise (kernels_b.cu)
 int launch_nbr_g(const int32_t *nbr_id, const double *nbr_w, double *nbr_g, int64_t count, double beta, int weighted,
                  cudaStream_t s);
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s);
-// Warp-specialised pipeline (kernels_b2.cu); *handled=false when the shape is outside its range.
-int launch_estep_pipe(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);
-// Bulk-copy pipeline (kernels_b3.cu), the default fast path; same contract.
+// Warp-specialised bulk-copy pipeline (estep_bulk.cuh, kernels_b3*.cu), the fast path; *handled=false when the
+// shape is outside its range.
 int launch_estep_bulk(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled);
 // Fold per-block partials into stats_out (defined in kernels_b.cu).
 int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, double *stats_out, cudaStream_t s);

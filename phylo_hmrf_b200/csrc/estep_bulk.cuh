@@ -24,8 +24,6 @@
 // (tools/swizzle_check.py), and a consumer addresses every operand of a step from
 // base ^ (step << 5) plus an immediate per 8-row tile.
 // exp() is a 2048-entry table (2^(j/2048), shared memory) times a quadratic: 6 FP64 instructions.
-#include <cstdlib>
-
 #pragma once
 #include "estep_common.cuh"
 
@@ -456,17 +454,6 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
                 }
             }
             const double g_li = *reinterpret_cast<double *>(eb + raw_li);
-            // one factor per slot: the label's whole product at its first slot, 1 at a repeat
-#pragma unroll
-            for (int s = 0; s < kFastSlots; ++s) {
-                const uint32_t o = (offp[s / 2] >> (16 * (s & 1))) & 0xffffu;
-                gw[s] = 1.0;
-                if (o != 0xffffu) {
-                    double *gp = reinterpret_cast<double *>(eb + o);
-                    gw[s] = *gp;
-                    *gp = 1.0;
-                }
-            }
             // ---- second use: the log-likelihood tile, one bulk copy
             fence_proxy_async();
             __syncwarp();
@@ -495,7 +482,8 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
                     *reinterpret_cast<double *>(ec + colo[u] + u * 256) = tb[u];
                 }
             }
-            {   // last 8-state chunk: KR live rows, the rest are padding states (zero weight)
+            {   // last 8-state chunk: KR live rows; the rest are padding states, whose rows arrive from HBM as
+                // 0.0 -- already the zero weight the statistics product needs (common.cuh logp_rows)
                 double tb[KR];
                 unsigned char *ec = eb + (NK8 - 1) * 2048;
 #pragma unroll
@@ -506,8 +494,6 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
                     esum += tb[u];
                     *reinterpret_cast<double *>(ec + colo[u] + u * 256) = tb[u];
                 }
-#pragma unroll
-                for (int u = KR; u < 8; ++u) *reinterpret_cast<double *>(ec + colo[u] + u * 256) = 0.0;
             }
             // the node's features: in flight while the neighbour factors are applied
             double x[D];
@@ -519,7 +505,7 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
                     px += ld;
                 }
             }
-            // e_k *= G_k for the labels met among the neighbours
+            // e_k *= g_s for every neighbour slot in turn (a label met twice is multiplied twice: the product)
 #pragma unroll
             for (int s = 0; s < kFastSlots; ++s) {
                 const uint32_t o = (offp[s / 2] >> (16 * (s & 1))) & 0xffffu;
@@ -724,16 +710,6 @@ int launch_bulk(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled)
     if constexpr (NK8 * C::NT * 2 > 64) {
         return PHMRF_OK;  // accumulator tiles would not fit the consumer's registers
     } else {
-        if constexpr ((D == 9 && NK8 == 4) || (D == 5 && NK8 == 3)) {  // tuning switch for the bench shapes
-            static const int force_p = [] {
-                const char *v = getenv("PHMRF_BULK_P");
-                return v ? atoi(v) : 0;
-            }();
-            if (force_p == 8 && C::P != 8) return launch_bulk_p<D, NK8, 8>(a, sm_count, s, handled);
-            if constexpr (D == 5) {
-                if (force_p == 12 && C::P != 12) return launch_bulk_p<D, NK8, 12>(a, sm_count, s, handled);
-            }
-        }
         return launch_bulk_p<D, NK8, C::P>(a, sm_count, s, handled);
     }
 }

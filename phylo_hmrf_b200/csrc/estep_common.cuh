@@ -1,4 +1,4 @@
-// Pieces shared by the two phase-B kernels (kernels_b.cu: general path; kernels_b2.cu:
+// Pieces shared by the two phase-B kernels (kernels_b.cu: general path; estep_bulk.cuh:
 // warp-specialised pipeline): register-tile geometry, compile-time feature rows, exp().
 #pragma once
 #include <cfloat>

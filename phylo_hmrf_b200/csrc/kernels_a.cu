@@ -512,12 +512,12 @@ int launch_check_labels(const int32_t *labels, int64_t n, int K, long long *firs
     return PHMRF_OK;
 }
 
-// zero the log-likelihood buffer and set the padding state rows K..KP-1 of every tile
+// zero the log-likelihood buffer; the padding row of an odd K gets kLogpPad (see common.cuh logp_rows)
 __global__ void logp_init_kernel(double *__restrict__ logp, int64_t ld, int K, int KP, double pad) {
     const int64_t total = (ld >> 5) * KP * 32;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)((e >> 5) % KP);
-        logp[e] = k < K ? 0.0 : pad;
+        logp[e] = (k == K && (K & 1)) ? pad : 0.0;
     }
 }
 

@@ -490,6 +490,24 @@ int launch_estep_finalize(const double *partials, int n_blocks, int K, int D, do
     return PHMRF_OK;
 }
 
+// g[s][i] = exp(beta * (weighted ? w[s][i] : 1)) for occupied neighbour slots, 1 otherwise: the per-slot
+// factors of the pipeline kernel for regions with an explicit graph; constant while beta and the weights are
+__global__ void nbr_g_kernel(const int32_t *__restrict__ nbr_id, const double *__restrict__ nbr_w,
+                             double *__restrict__ nbr_g, int64_t count, double beta, int weighted) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        nbr_g[i] = nbr_id[i] >= 0 ? exp(beta * (weighted ? nbr_w[i] : 1.0)) : 1.0;
+}
+
+int launch_nbr_g(const int32_t *nbr_id, const double *nbr_w, double *nbr_g, int64_t count, double beta, int weighted,
+                 cudaStream_t s) {
+    if (count <= 0) return PHMRF_OK;
+    const int64_t blocks = (count + 255) / 256;
+    nbr_g_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, s>>>(nbr_id, nbr_w, nbr_g, count, beta, weighted);
+    count_launch();
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
+}
+
 int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s) {
     if (a.n == 0) {
         PHMRF_CUDA(cudaMemsetAsync(a.stats_out, 0, sizeof(double) * (a.K * (1 + a.D + a.D * a.D) + 3), s));
@@ -497,12 +515,7 @@ int launch_estep(const EstepArgs &a, int sm_count, cudaStream_t s) {
     }
     if (!a.force_general) {
         bool handled = false;
-        // PHMRF_ESTEP_KERNEL=r1 selects the round-1 pipeline (kernels_b2.cu), kept for A/B timing
-        static const bool use_r1 = [] {
-            const char *v = getenv("PHMRF_ESTEP_KERNEL");
-            return v != nullptr && v[0] == 'r' && v[1] == '1';
-        }();
-        int rc = use_r1 ? launch_estep_pipe(a, sm_count, s, &handled) : launch_estep_bulk(a, sm_count, s, &handled);
+        int rc = launch_estep_bulk(a, sm_count, s, &handled);
         if (rc != PHMRF_OK || handled) return rc;
     }
     switch (a.D) {

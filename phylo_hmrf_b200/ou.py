@@ -238,8 +238,9 @@ def fit_cluster(tree, obs, mean_values, magnitude, min_covar, rng):
     for _ in range(11):
         guess = init_guess(tree, mean_values, magnitude, rng)
         try:
-            res = minimize(lambda p: single_objective(tree, p, obs, min_covar)[0], guess, constraints=_BOX, tol=1e-6,
-                           options={'disp': False})
+            with np.errstate(over='ignore', invalid='ignore', divide='ignore'):   # probes outside the box
+                res = minimize(lambda p: single_objective(tree, p, obs, min_covar)[0], guess, constraints=_BOX,
+                               tol=1e-6, options={'disp': False})
         except Exception:
             continue
         params = res.x
@@ -257,7 +258,11 @@ def optimise_state(tree, state_id, stats, n_samples, lambda_0, min_covar, init_p
     from scipy.optimize import minimize
 
     def objective(p):
-        return mstep_objective(tree, p, state_id, stats, n_samples, lambda_0, min_covar, init_params)[0]
+        # SLSQP probes points outside the [0,100] box the constraints describe (the reference's optimiser
+        # does the same, phylo_hmrf.py:1365-1383): exp(-beta) overflows there and the objective comes back
+        # inf/NaN, which the line search rejects -- evaluate quietly instead of warning on every probe
+        with np.errstate(over='ignore', invalid='ignore', divide='ignore'):
+            return mstep_objective(tree, p, state_id, stats, n_samples, lambda_0, min_covar, init_params)[0]
 
     for _ in range(11):
         if initial_mode == 1:

@@ -11,7 +11,7 @@ for f in kernels_b3 kernels_b3_d58 kernels_b3_d9c; do
 done
 wait
 OBJS=""
-for f in api kernels_a kernels_b kernels_b2 kernels_grid kernels_prep probe; do OBJS="$OBJS $PKG/build/$f.cu.o"; done
+for f in api kernels_a kernels_b kernels_grid kernels_prep probe; do OBJS="$OBJS $PKG/build/$f.cu.o"; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libphmrf.so $OBJS $OUT/kernels_b3.o $OUT/kernels_b3_d58.o $OUT/kernels_b3_d9c.o
 python - $OUT <<'PY'
 import re, sys, glob

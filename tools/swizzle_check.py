@@ -2,7 +2,7 @@
 section 8, item 1a): a tile is [K rows][32 nodes] doubles at row stride 32, node n of state row k stored at
 column n ^ (4 * (k & 7)).  Checks, by enumeration of the shared-memory banks (32 banks x 4 B; a 64-bit
 access is served per half-warp):
-  * the DMMA A-operand load of kernels_b2.cu (lane g = lane/4, t = lane%4 reads state 8*kt+g, node 4*ns+t),
+  * the DMMA A-operand load of estep_bulk.cuh (lane g = lane/4, t = lane%4 reads state 8*kt+g, node 4*ns+t),
   * the producers' column access (lane = node, one state row at a time),
   * that four consecutive nodes stay contiguous (the emission kernel's 32-byte stores),
 are conflict-free / contiguous for every state tile and k-step.  Pure CPU; prints OK or the first conflict."""
