@@ -74,66 +74,125 @@ __global__ void scatter_kernel(const double *__restrict__ value, const int64_t *
     }
 }
 
-// median of the 8 neighbours = mean of the 4th and 5th smallest (numpy.median of an even count)
+// median of the 8 neighbours = mean of the 4th and 5th smallest (numpy.median of an even count).
+// A 17-comparator selection network of depth 6 (the 19-comparator sorting network for 8 keys with the two
+// exchanges that cannot reach outputs 3 and 4 removed; checked exhaustively with the 0-1 principle): the
+// hole fill is a chain of dependent steps, so the DEPTH of the network is what its run time is made of.
+__device__ __forceinline__ void cmpx(double &a, double &b) {
+    const double lo = fmin(a, b), hi = fmax(a, b);
+    a = lo;
+    b = hi;
+}
 __device__ __forceinline__ double median8(double (&w)[8]) {
-#pragma unroll
-    for (int a = 1; a < 8; ++a) {
-#pragma unroll
-        for (int b = a; b > 0; --b) {
-            const double lo = fmin(w[b - 1], w[b]), hi = fmax(w[b - 1], w[b]);
-            w[b - 1] = lo;
-            w[b] = hi;
-        }
-    }
-    return __ddiv_rn(__dadd_rn(w[3], w[4]), 2.0);
+    cmpx(w[0], w[1]); cmpx(w[2], w[3]); cmpx(w[4], w[5]); cmpx(w[6], w[7]);
+    cmpx(w[0], w[2]); cmpx(w[1], w[3]); cmpx(w[4], w[6]); cmpx(w[5], w[7]);
+    cmpx(w[1], w[2]); cmpx(w[5], w[6]); cmpx(w[0], w[4]); cmpx(w[3], w[7]);
+    cmpx(w[1], w[5]); cmpx(w[2], w[6]);
+    cmpx(w[2], w[4]); cmpx(w[3], w[5]);
+    cmpx(w[3], w[4]);
+    return __dmul_rn(__dadd_rn(w[3], w[4]), 0.5);  // = (a+b)/2 correctly rounded, without the division routine
 }
 
-// 3x3 median hole fill in the reference's sequential raster order.  Cell (i,j) reads row i-1,
-// (i,j-1) -- already updated -- and (i,j+1), row i+1 -- not yet updated.  All cells with the same
-// t = 2i + j are independent and every updated neighbour has a smaller t, so sweeping t in order
-// with a barrier in between reproduces the sequential result exactly.  One CTA per plane.
-// symmetric != 0: only the upper triangle (j >= i) is scanned and a cell below the diagonal is
-// read through its mirror, which is what the reference's mirrored writes amount to on a
-// symmetric image (utility.py:603-630); the lower triangle is rewritten afterwards.
-__global__ void __launch_bounds__(1024) holefill_kernel(double *__restrict__ planes, int64_t plane_stride, int64_t n1,
-                                                        int64_t n2, int symmetric) {
-    double *P = planes + (int64_t)blockIdx.x * plane_stride;
+// 3x3 median hole fill in the reference's sequential raster order (utility.py:603-659).  Cell (i,j)
+// reads row i-1 and (i,j-1) -- already updated -- and (i,j+1), row i+1 -- not yet updated.  In the
+// skewed coordinates (i, s = i + j) every updated neighbour has a smaller or equal i AND a smaller or
+// equal s, and every not-yet-updated one a larger or equal i and s; so the (i, s) plane can be cut
+// into rectangular tiles (kHfR rows x kHfC skewed columns), a tile depends only on its upper, left
+// and upper-left neighbours, and all tiles with the same I + S are independent: one launch per tile
+// anti-diagonal, one warp per tile.  Inside a tile the cells with equal ri + si (= the 2i + j fronts
+// of the unskewed image) are independent as well: lane = row, kHfR + kHfC - 1 steps with a warp
+// barrier, on a shared-memory copy of the tile's bounding box (row stride odd: conflict free).  The
+// result equals the sequential scan bit for bit (tests/test_prep_oracle.py replays this schedule on
+// the CPU; tests/test_gpu_prep.py compares with the reference's fixtures).
+// symmetric != 0: only the upper triangle (j >= i) is scanned and a cell below the diagonal is read
+// through its mirror, which is what the reference's mirrored writes amount to on a symmetric image;
+// the lower triangle is rewritten afterwards (mirror_kernel).
+// (Round 1 swept the 2i+j fronts of the WHOLE image with one CTA per plane: 3W block barriers and one
+// 32-byte sector per cell, 117 ms at W = 8192.)
+constexpr int kHfR = 32, kHfC = 64;
+constexpr int kHfBH = kHfR + 2, kHfBW = kHfC + kHfR + 1;  // bounding box incl. the one-cell halo; width odd
+constexpr int kHfThreads = 128;  // four warps fetch the bounding box (the loads are the latency), warp 0 sweeps the tile
+
+__global__ void __launch_bounds__(kHfThreads) holefill_tile_kernel(double *__restrict__ planes, int64_t plane_stride, int64_t n1,
+                                                           int64_t n2, int symmetric, int w, int I_lo) {
+    __shared__ double tile[kHfBH][kHfBW];
+    const int I = I_lo + (int)blockIdx.x, S = w - I;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *P = planes + (int64_t)blockIdx.y * plane_stride;
+    const int64_t i0 = (int64_t)I * kHfR, s0 = (int64_t)S * kHfC;
     const int64_t i_lo = 2, i_hi = n1 - 2, j_hi = n2 - 2;  // inclusive bounds of range(2, n-1)
-    if (i_hi < i_lo || j_hi < 2) return;
-    const int64_t j_lo0 = 2;
-    const int64_t t_first = 2 * i_lo + (symmetric ? i_lo : j_lo0), t_last = 2 * i_hi + j_hi;
-    for (int64_t t = t_first; t <= t_last; ++t) {
-        // rows with a cell on this front: j = t - 2i within [jmin(i), j_hi]
-        int64_t ia = (t - j_hi + 1) / 2;  // ceil((t - j_hi) / 2) for t - j_hi >= 0
-        if (t - j_hi < 0) ia = i_lo;
-        ia = ia < i_lo ? i_lo : ia;
-        int64_t ib = symmetric ? t / 3 : (t - j_lo0) / 2;
-        ib = ib > i_hi ? i_hi : ib;
-        for (int64_t i = ia + threadIdx.x; i <= ib; i += blockDim.x) {
-            const int64_t j = t - 2 * i;
-            const double v = P[i * n2 + j];
-            if (v < kThresh) {
-                double w[8];
-                int q = 0;
+    // does the tile hold any cell of the scan?  rows [i0, i0+R) x columns j = s - i
+    const int64_t ra = i0 > i_lo ? i0 : i_lo, rb = (i0 + kHfR - 1) < i_hi ? (i0 + kHfR - 1) : i_hi;
+    if (ra > rb) return;
+    if (s0 + kHfC - 1 - ra < (symmetric ? ra : 2)) return;  // largest j of the tile (at its first scanned row)
+    if (s0 - rb > j_hi) return;                             // smallest j of the tile (at its last scanned row)
+    const int64_t bi0 = i0 - 1, bj0 = s0 - (i0 + kHfR - 1) - 1;
+    constexpr int kCols = (kHfBW + 31) / 32;
+#pragma unroll 3
+    for (int r = warp; r < kHfBH; r += kHfThreads / 32) {
+        const int64_t gi = bi0 + r;
+        double v[kCols];
 #pragma unroll
-                for (int di = -1; di <= 1; ++di)
+        for (int q = 0; q < kCols; ++q) {  // all loads of a row in flight before the first store
+            const int c = lane + 32 * q;
+            const int64_t gj = bj0 + c;
+            v[q] = (c < kHfBW && gi >= 0 && gi < n1 && gj >= 0 && gj < n2) ? P[gi * n2 + gj] : 0.0;
+        }
 #pragma unroll
-                    for (int dj = -1; dj <= 1; ++dj) {
-                        if (di == 0 && dj == 0) continue;
-                        int64_t a = i + di, b = j + dj;
-                        if (symmetric && a > b) {
-                            const int64_t s = a;
-                            a = b;
-                            b = s;
+        for (int q = 0; q < kCols; ++q)
+            if (lane + 32 * q < kHfBW) tile[r][lane + 32 * q] = v[q];
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const int64_t i = i0 + lane;
+    const bool row_ok = i >= i_lo && i <= i_hi;
+    const int64_t j_lo = symmetric ? i : 2;
+    for (int d = 0; d < kHfR + kHfC - 1; ++d) {
+        const int si = d - lane;
+        if (row_ok && si >= 0 && si < kHfC) {
+            const int64_t j = s0 + si - i;
+            if (j >= j_lo && j <= j_hi) {
+                const int r = lane + 1, c = (int)(j - bj0);
+                if (tile[r][c] < kThresh) {
+                    double nb[8];
+                    int q = 0;
+#pragma unroll
+                    for (int di = -1; di <= 1; ++di)
+#pragma unroll
+                        for (int dj = -1; dj <= 1; ++dj) {
+                            if (di == 0 && dj == 0) continue;
+                            int64_t a = i + di, b = j + dj;
+                            if (symmetric && a > b) {
+                                const int64_t t = a;
+                                a = b;
+                                b = t;
+                            }
+                            nb[q++] = tile[(int)(a - bi0)][(int)(b - bj0)];
                         }
-                        w[q++] = P[a * n2 + b];
+                    const double m1 = median8(nb);
+                    if (m1 > kThresh) {
+                        tile[r][c] = m1;
+                        P[i * n2 + j] = m1;
                     }
-                const double m1 = median8(w);
-                if (m1 > kThresh) P[i * n2 + j] = m1;
+                }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
+}
+
+// every tile anti-diagonal in turn (stream order is the only synchronisation between them)
+static int launch_holefill(double *planes, int64_t plane_stride, int nb, int64_t n1, int64_t n2, int symmetric,
+                           cudaStream_t s) {
+    if (n1 - 2 < 2 || n2 - 2 < 2) return PHMRF_OK;
+    const int NI = (int)((n1 + kHfR - 1) / kHfR), NS = (int)((n1 + n2 - 1 + kHfC - 1) / kHfC);
+    for (int w = 0; w < NI + NS - 1; ++w) {
+        const int I_lo = w - NS + 1 > 0 ? w - NS + 1 : 0, I_hi = w < NI - 1 ? w : NI - 1;
+        holefill_tile_kernel<<<dim3(I_hi - I_lo + 1, nb), kHfThreads, 0, s>>>(planes, plane_stride, n1, n2, symmetric, w, I_lo);
+    }
+    count_launch(NI + NS - 1);
+    PHMRF_CUDA(cudaGetLastError());
+    return PHMRF_OK;
 }
 
 __global__ void mirror_kernel(double *__restrict__ P, int64_t n) {
@@ -336,8 +395,11 @@ extern "C" int phmrf_prep_region_image(int device, const double *value, const in
         for (int q = 0; q < nb; ++q)
             scatter_kernel<<<grid_for(n), 256>>>(dval.as<double>(), dpos.as<int64_t>(), n, d, c0 + q, start1, start2, n1,
                                                  n2, kind == 1, dplane.as<double>() + (int64_t)q * npix, dbad.as<int>());
-        holefill_kernel<<<nb, 1024>>>(dplane.as<double>(), npix, n1, n2, kind == 1);
-        count_launch(nb + 1);
+        count_launch(nb);
+        {
+            const int rc_fill = launch_holefill(dplane.as<double>(), npix, nb, n1, n2, kind == 1, nullptr);
+            if (rc_fill != PHMRF_OK) return rc_fill;
+        }
         for (int q = 0; q < nb; ++q) {
             const int c = c0 + q;
             double *plane = dplane.as<double>() + (int64_t)q * npix;

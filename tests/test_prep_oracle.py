@@ -106,6 +106,61 @@ def test_wavefront_schedule_equals_the_sequential_scan(name):
     np.testing.assert_array_equal(_wavefront_fill(r, False), po.near_interpolation1a(r.copy()))
 
 
+def _tiled_fill(m, symmetric, R=4, C=6, reverse=False):
+    """The schedule of holefill_tile_kernel restated with NumPy: the skewed plane (i, s = i + j) cut into
+    R x C tiles, tile anti-diagonals I + S in turn, the tiles of one anti-diagonal in ANY order (they must be
+    independent: `reverse` flips it), the cells of a tile by their own anti-diagonals ri + si from a snapshot."""
+    m = m.copy()
+    n1, n2 = m.shape
+    i_hi, j_hi = n1 - 2, n2 - 2
+    NI, NS = -(-n1 // R), -(-(n1 + n2 - 1) // C)
+    for w in range(NI + NS - 1):
+        tiles = [(I, w - I) for I in range(max(0, w - NS + 1), min(NI - 1, w) + 1)]
+        for I, S in (reversed(tiles) if reverse else tiles):
+            for d in range(R + C - 1):
+                snap = m.copy()
+                for ri in range(R):
+                    si = d - ri
+                    i = I * R + ri
+                    if not (0 <= si < C) or i < 2 or i > i_hi:
+                        continue
+                    j = S * C + si - i
+                    if j < (i if symmetric else 2) or j > j_hi or snap[i, j] >= po.THRESH1:
+                        continue
+                    w8 = []
+                    for di in (-1, 0, 1):
+                        for dj in (-1, 0, 1):
+                            if di or dj:
+                                a, b = i + di, j + dj
+                                if symmetric and a > b:
+                                    a, b = b, a
+                                w8.append(snap[a, b])
+                    med = np.median(w8)
+                    if med > po.THRESH1:
+                        m[i, j] = med
+    if symmetric:
+        iu = np.triu_indices(n1, 1)
+        m[(iu[1], iu[0])] = m[iu]
+    return m
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_tiled_skewed_schedule_equals_the_sequential_scan(reverse):
+    """holefill_tile_kernel's order (tiles of the skewed plane, anti-diagonal by anti-diagonal) must give the
+    reference's in-place raster-scan result, whichever way the tiles of one anti-diagonal are ordered."""
+    rng = np.random.default_rng(11)
+    for n, dens in ((31, 0.45), (23, 0.3), (40, 0.6)):   # sparse images: long fill cascades, also across the diagonal
+        s = rng.random((n, n)) * (rng.random((n, n)) < dens)
+        s = np.triu(s) + np.triu(s, 1).T
+        np.testing.assert_array_equal(_tiled_fill(s, True, reverse=reverse), po.near_interpolation1(s.copy()))
+    for shape, dens in (((19, 27), 0.5), ((33, 14), 0.35)):
+        r = rng.random(shape) * (rng.random(shape) < dens)
+        np.testing.assert_array_equal(_tiled_fill(r, False, reverse=reverse), po.near_interpolation1a(r.copy()))
+    for name in NAMES:                                    # and the reference's own fixtures
+        p = "prep_%s_" % name
+        np.testing.assert_array_equal(_tiled_fill(G[p + "rect"], False, R=3, C=5, reverse=reverse), G[p + "rect_filled"])
+
+
 def test_host_side_argument_checks_need_no_gpu():
     """The utility.py mirrors validate their arguments before any device call."""
     from phylo_hmrf_b200 import utility
