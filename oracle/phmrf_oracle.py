@@ -4,7 +4,7 @@ This module is a Python-3 / NumPy restatement of the reference's per-region
 E-step arithmetic.  It is the *checker* the CUDA path is compared against.
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import it; nothing under ``phylo_hmrf_b200/``
-does (tests/test_no_oracle_in_product.py enforces that).
+does (tests/test_abi.py::test_product_never_imports_oracle enforces that).
 
 Parity anchoring
 ----------------
