@@ -102,7 +102,7 @@ __device__ __forceinline__ double median8(double (&w)[8]) {
 // anti-diagonal, one warp per tile.  Inside a tile the cells with equal ri + si (= the 2i + j fronts
 // of the unskewed image) are independent as well: lane = row, kHfR + kHfC - 1 steps with a warp
 // barrier, on a shared-memory copy of the tile's bounding box (row stride odd: conflict free).  The
-// result equals the sequential scan bit for bit (tests/test_prep_oracle.py replays this schedule on
+// result equals the sequential scan bit for bit (the CPU test tier replays this schedule on
 // the CPU; tests/test_gpu_prep.py compares with the reference's fixtures).
 // symmetric != 0: only the upper triangle (j >= i) is scanned and a cell below the diagonal is read
 // through its mirror, which is what the reference's mirrored writes amount to on a symmetric image;
