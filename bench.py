@@ -407,6 +407,8 @@ def run_ours(args):
         "kernel": "estep_bulk_kernel (phase B: posteriors+costs+statistics, csrc/estep_bulk.cuh)",
         "traffic": ncu_traffic(args.workload, "estep"),
         "peak_source": "FP64: DFMA-chain probe in this run (csrc/probe.cu); HBM: %s" % hbm_src,
+        # MEASURED_PEAKS.json has no FP64 figure; the nominal peak (148 SMs x 64 DFMA/clk x 2 x 1.965 GHz) for comparison
+        "fp64_peak_nominal": 37.2, "frac_of_nominal_fp64": (b_tflops / 37.2) if bound == "fp64" else None,
         "algorithmic_per_launch": {"flops": n_rank * K * estep_flops_per_node_state(d), "bytes": b_bytes},
         "kernel_share_of_step": phase_ms[2] / phase_ms.sum(),
         "phase_ms": {"A1_emit": phase_ms[0], "A2_quantise": phase_ms[1], "B_estep": phase_ms[2],
