@@ -54,6 +54,19 @@ def test_no_cpu_fallback_without_gpu(built):
         ph.log_multivariate_normal_density(np.zeros((4, 3)), np.zeros((2, 3)), np.stack([np.eye(3)] * 2))
 
 
+def test_host_staging_needs_a_device_and_rejects_nonsense(built):
+    """phmrf_host_alloc: error code (never a crash) without a CUDA device; bad arguments are rejected."""
+    import torch
+    from phylo_hmrf_b200 import _lib, engine
+    p = C.c_void_p()
+    assert _lib.lib().phmrf_host_alloc(-1, C.byref(p)) == -1
+    assert _lib.lib().phmrf_host_free(None) == 0
+    if not torch.cuda.is_available():
+        assert _lib.lib().phmrf_host_alloc(1024, C.byref(p)) == -2 and not p.value
+        with pytest.raises(_lib.PhmrfError):
+            engine.pinned_empty((4, 4), np.int32)
+
+
 def test_invalid_arguments_are_rejected(built):
     from phylo_hmrf_b200 import _lib
     h = C.c_void_p()
