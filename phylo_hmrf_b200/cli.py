@@ -77,6 +77,8 @@ def _launch_context(device):
     torch.cuda.set_device(local)
     if not td.is_initialized():
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import atexit
+        atexit.register(lambda: td.is_initialized() and td.destroy_process_group())
     return local, td.get_rank(), world, td
 
 
