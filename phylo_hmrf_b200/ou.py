@@ -273,7 +273,8 @@ def optimise_state(tree, state_id, stats, n_samples, lambda_0, min_covar, init_p
             rnd = magnitude * rng.random(tree.n_params)
         guess = w_init * init_params + w_cur * current_params + (1 - w_init - w_cur) * rnd
         try:
-            res = minimize(objective, guess, method='SLSQP', constraints=_BOX, tol=1e-6, options={'disp': False})
+            with np.errstate(over='ignore', invalid='ignore', divide='ignore'):   # finite differences through inf probes
+                res = minimize(objective, guess, method='SLSQP', constraints=_BOX, tol=1e-6, options={'disp': False})
         except Exception:
             continue
         if tree.check_params(res.x) > 0:
