@@ -144,37 +144,50 @@ __global__ void __launch_bounds__(kHfThreads) holefill_tile_kernel(double *__res
     }
     __syncthreads();
     if (warp != 0) return;
+    // lane = row; at step d the lane's cell sits at bounding-box column c = d - 2*lane + kHfR (one column further
+    // per step).  Everything that does not change along the row is worked out once: the columns of the row that
+    // belong to this tile AND to the scan, the column up to which a neighbour may lie below the diagonal (read
+    // through its mirror), the row's address in the plane.
     const int64_t i = i0 + lane;
     const bool row_ok = i >= i_lo && i <= i_hi;
-    const int64_t j_lo = symmetric ? i : 2;
-    for (int d = 0; d < kHfR + kHfC - 1; ++d) {
-        const int si = d - lane;
-        if (row_ok && si >= 0 && si < kHfC) {
-            const int64_t j = s0 + si - i;
-            if (j >= j_lo && j <= j_hi) {
-                const int r = lane + 1, c = (int)(j - bj0);
-                if (tile[r][c] < kThresh) {
-                    double nb[8];
-                    int q = 0;
+    const int64_t j_first = symmetric ? i : 2;
+    int c_min = kHfR - lane, c_max = kHfR - lane + kHfC - 1;                 // the tile's own skewed columns
+    if (j_first - bj0 > c_min) c_min = (int)(j_first - bj0);                  // the scan's range of j
+    if (j_hi - bj0 < c_max) c_max = (int)(j_hi - bj0);
+    if (!row_ok) c_max = c_min - 1;
+    const int c_diag = symmetric ? (int)(i + 1 - bj0) : -1;                   // j <= i + 1: a neighbour has a > b
+    double *const Prow = P + i * n2 + bj0;
+    double *const trow = &tile[lane + 1][0];
+    int c = kHfR - 2 * lane;
+    for (int d = 0; d < kHfR + kHfC - 1; ++d, ++c) {
+        if (c >= c_min && c <= c_max && trow[c] < kThresh) {
+            double nb[8];
+            if (c > c_diag) {                       // all eight neighbours on or above the diagonal: fixed offsets
+                const double *q = trow + c;
+                nb[0] = q[-kHfBW - 1]; nb[1] = q[-kHfBW]; nb[2] = q[-kHfBW + 1];
+                nb[3] = q[-1];                            nb[4] = q[1];
+                nb[5] = q[kHfBW - 1];  nb[6] = q[kHfBW];  nb[7] = q[kHfBW + 1];
+            } else {
+                const int64_t j = c + bj0;
+                int q = 0;
 #pragma unroll
-                    for (int di = -1; di <= 1; ++di)
+                for (int di = -1; di <= 1; ++di)
 #pragma unroll
-                        for (int dj = -1; dj <= 1; ++dj) {
-                            if (di == 0 && dj == 0) continue;
-                            int64_t a = i + di, b = j + dj;
-                            if (symmetric && a > b) {
-                                const int64_t t = a;
-                                a = b;
-                                b = t;
-                            }
-                            nb[q++] = tile[(int)(a - bi0)][(int)(b - bj0)];
+                    for (int dj = -1; dj <= 1; ++dj) {
+                        if (di == 0 && dj == 0) continue;
+                        int64_t a = i + di, b = j + dj;
+                        if (a > b) {
+                            const int64_t t = a;
+                            a = b;
+                            b = t;
                         }
-                    const double m1 = median8(nb);
-                    if (m1 > kThresh) {
-                        tile[r][c] = m1;
-                        P[i * n2 + j] = m1;
+                        nb[q++] = tile[(int)(a - bi0)][(int)(b - bj0)];
                     }
-                }
+            }
+            const double m1 = median8(nb);
+            if (m1 > kThresh) {
+                trow[c] = m1;
+                Prow[c] = m1;
             }
         }
         __syncwarp();
