@@ -435,7 +435,7 @@ def run_ours(args):
     })
     cpu = cpu_vec = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(d, K, bins[0], seconds=args.cpu_seconds)
+        cpu = cpu_baseline(d, K, bins[0], seconds=args.cpu_seconds, full_regions=bins if wl["cfg"] in (1, 2) else None)
         cpu_vec = cpu_vectorised(d, K, bins[0])
     resident = sum(p.n * (d * 8 + K * 8 + 96) for p in pieces) / 1e9
     out = {
@@ -633,9 +633,11 @@ def _cpu_region(args):
 
 def cpu_sample(d, K, B_crop, n_regions, B0, faithful=True):
     """One 'iteration' of the reference's CPU path: one process per region (base.py:357-362),
-    each running the loop-faithful restatement of _predict_posteriors minus the graph cut."""
+    each running the loop-faithful restatement of _predict_posteriors minus the graph cut.
+    B_crop: bins of every region (int) or one entry per region (list)."""
     import multiprocessing as mp
-    jobs = [(900 + r, B_crop, d, K, B0, faithful) for r in range(n_regions)]
+    sizes = list(B_crop) if isinstance(B_crop, (list, tuple)) else [B_crop] * n_regions
+    jobs = [(900 + r, sizes[r], d, K, B0, faithful) for r in range(n_regions)]
     t0 = time.perf_counter()
     if n_regions == 1:
         res = [_cpu_region(jobs[0])]
@@ -647,7 +649,14 @@ def cpu_sample(d, K, B_crop, n_regions, B0, faithful=True):
     return nodes, wall, max(r[1] for r in res)
 
 
-def cpu_baseline(d, K, B0, seconds=15.0):
+def cpu_baseline(d, K, B0, seconds=15.0, full_regions=None):
+    if full_regions:      # configs 1-2 are timed IN FULL: every region whole, one process per region
+        nodes, wall, inner = cpu_sample(d, K, list(full_regions), len(full_regions), B0)
+        return {"value": nodes * K / inner, "unit": UNIT, "cores": len(full_regions), "kind": "port",
+                "sample": "the whole configuration: %d region(s) of %s bins (%d nodes), d=%d K=%d, one forked process per "
+                          "region like base.py:357-362 (the reference's own parallel width); loop-faithful Python-3 "
+                          "restatement of phylo_hmrf.py:297-468 (the py2 reference cannot run here); GCO excluded"
+                          % (len(full_regions), list(full_regions), nodes, d, K)}
     cores = min(os.cpu_count() or 1, 32)
     B_crop = 60
     nodes, wall, inner = cpu_sample(d, K, B_crop, cores, B0)
