@@ -657,18 +657,16 @@ def cpu_baseline(d, K, B0, seconds=15.0, full_regions=None):
                           "region like base.py:357-362 (the reference's own parallel width); loop-faithful Python-3 "
                           "restatement of phylo_hmrf.py:297-468 (the py2 reference cannot run here); GCO excluded"
                           % (len(full_regions), list(full_regions), nodes, d, K)}
+    # configs 3-5: the 2e5-node crop BASELINE.md section 4(5) plans (a 632-bin triangle = 200 028 nodes), one per core --
+    # a rate, the path is linear in N.  (The reference itself would give ONE process to a one-region configuration.)
     cores = min(os.cpu_count() or 1, 32)
-    B_crop = 60
+    B_crop = 632 if seconds >= 10 else 60
     nodes, wall, inner = cpu_sample(d, K, B_crop, cores, B0)
-    reps = max(1, int(seconds / max(wall, 1e-3)) - 1)
-    best = inner
-    for _ in range(min(reps, 3)):
-        nodes, wall, inner = cpu_sample(d, K, B_crop, cores, B0)
-        best = min(best, inner)
-    return {"value": nodes * K / best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d regions of a %d-bin triangle (%d nodes total), d=%d K=%d, one forked process per region "
-                      "like base.py:357-362; loop-faithful Python-3 restatement of phylo_hmrf.py:297-468 "
-                      "(the py2 reference cannot run here); GCO excluded" % (cores, B_crop, nodes, d, K)}
+    return {"value": nodes * K / inner, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d regions of a %d-bin triangle (%d nodes each, %d in total), d=%d K=%d, one forked process per "
+                      "region like base.py:357-362; loop-faithful Python-3 restatement of phylo_hmrf.py:297-468 "
+                      "(the py2 reference cannot run here); GCO excluded; %.1f s of wall time"
+                      % (cores, B_crop, nodes // cores, nodes, d, K, wall)}
 
 
 def cpu_vectorised(d, K, B0):
