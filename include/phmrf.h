@@ -204,6 +204,14 @@ int64_t phmrf_region_n_window(const phmrf_region *r);
 int64_t phmrf_region_own_offset(const phmrf_region *r);
 int phmrf_region_edges(phmrf_region *r, int64_t *edge_ids_out, double *edge_w_out);
 
+/* For a region built by phmrf_region_create_grid whose edge list the caller ALSO holds as the reference's
+ * host arrays (output of _edge_weight_undirected_vec, phylo_hmrf.py:567-598): hand over the host's
+ * w = exp(-beta1*d_ij) [E] (same order as phmrf_region_edges).  The integer conversion of the edge weights
+ * (phmrf_quantise) and max|w| then use exactly these values -- NumPy's exp and the device's may differ in
+ * the last bit, and the integer arrays handed to the graph cut must be those pygco would build from the
+ * host array -- while phase B keeps the device-built weights of the implicit grid. */
+int phmrf_region_set_edge_weights(phmrf_region *r, const double *edge_w, int64_t n_edges);
+
 /* ------------------------------------------------------------------ preprocessing ----- */
 
 /* Per-species rescale to a common range followed by the log transform (utility.py:867-897

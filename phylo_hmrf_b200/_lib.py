@@ -71,6 +71,7 @@ SIGNATURES = {
     "phmrf_region_n_window": (C.c_int64, [_vp]),
     "phmrf_region_own_offset": (C.c_int64, [_vp]),
     "phmrf_region_edges": (C.c_int, [_vp, _c_int64_p, _c_double_p]),
+    "phmrf_region_set_edge_weights": (C.c_int, [_vp, _c_double_p, C.c_int64]),
     "phmrf_grid_edge_count": (C.c_int64, [C.c_int, C.c_int64, C.c_int64, C.c_int]),
     "phmrf_grid_edges": (C.c_int, [C.c_int, _c_double_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _c_double_p,
                                    C.c_int64]),

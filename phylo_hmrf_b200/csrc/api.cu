@@ -578,6 +578,31 @@ int phmrf_region_edges(phmrf_region *r, int64_t *edge_ids_out, double *edge_w_ou
     return PHMRF_OK;
 }
 
+int phmrf_region_set_edge_weights(phmrf_region *r, const double *edge_w, int64_t n_edges) {
+    if (!r || (n_edges > 0 && !edge_w) || n_edges != r->E) {
+        set_error("phmrf_region_set_edge_weights: need the region's own number of edge weights");
+        return PHMRF_E_INVALID;
+    }
+    if (!r->d_fwd) {
+        set_error("phmrf_region_set_edge_weights: only for regions built by phmrf_region_create_grid");
+        return PHMRF_E_STATE;
+    }
+    int rc = set_device(r->ctx);
+    if (rc) return rc;
+    double wmax = 0.0;
+    for (int64_t e = 0; e < n_edges; ++e) {
+        const double aw = std::fabs(edge_w[e]);
+        if (aw > wmax || std::isnan(aw)) wmax = aw;
+    }
+    if (n_edges > 0) {
+        PHMRF_CUDA(cudaMemcpyAsync(r->d_edge_w, edge_w, sizeof(double) * n_edges, cudaMemcpyHostToDevice, r->stream));
+        PHMRF_CUDA(cudaStreamSynchronize(r->stream));
+    }
+    r->wmax = wmax;
+    r->have_unary = false;
+    return PHMRF_OK;
+}
+
 int phmrf_region_update_X(phmrf_region *r, const double *X) {
     if (!r || (!X && r->n > 0)) return PHMRF_E_INVALID;
     int rc = set_device(r->ctx);

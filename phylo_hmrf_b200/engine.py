@@ -262,6 +262,12 @@ class GridRegion(Region):
         self.own_offset = int(L.phmrf_region_own_offset(h))
         self.n_edges = int(L.phmrf_region_n_edges(h))
 
+    def set_edge_weights(self, edge_w):
+        """Use the caller's host edge weights (same order as edges()) for the integer conversion; see
+        phmrf_region_set_edge_weights."""
+        w = as_f64(edge_w).reshape(-1)
+        check(_lib.lib().phmrf_region_set_edge_weights(self._h, dptr(w), len(w)))
+
     def edges(self):
         """-> (edge_ids [E,2] int64 window-local, edge_w [E]) for the host graph cut."""
         ids = np.empty((self.n_edges, 2), dtype=np.int64)

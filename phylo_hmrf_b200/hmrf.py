@@ -56,7 +56,7 @@ class phyloHMRF(object):
                  covariance_type='full', min_covar=1e-3, startprob_prior=1.0, transmat_prior=1.0, means_prior=0,
                  means_weight=0, covars_prior=1e-2, covars_weight=1, algorithm="viterbi", random_state=None,
                  n_iter=10, tol=1e-2, verbose=False, params="stmc", init_params="stmc", learning_rate=0.001,
-                 device=0):
+                 device=0, implicit_grid=True):
         if covariance_type != 'full':
             raise ValueError("the device path implements covariance_type='full' (phylo_hmrf.py:57)")
         self.n_components = int(n_components)
@@ -72,6 +72,7 @@ class phyloHMRF(object):
         self.edge_list_vec = edge_list_1
         self.len_vec = len_vec
         self.device = device
+        self.implicit_grid = bool(implicit_grid)   # regions whose edge list IS the grid's take the implicit-grid kernels
 
         self._model = engine.Model(self.n_components, self.n_features, device)
         self._regions = []
@@ -160,11 +161,35 @@ class phyloHMRF(object):
             if r not in owned:
                 self._regions.append(None)
                 continue
-            reg = self._model.region(np.asarray(X)[s1:s2], ids, w)
+            reg = self._grid_region(np.asarray(X)[s1:s2], len_vec[r], ids, w) if getattr(self, "implicit_grid", True) else None
+            if reg is None:
+                reg = self._model.region(np.asarray(X)[s1:s2], ids, w)
             reg._x_where = self._where(np.asarray(X)[s1:s2])
             reg._host_logprob = None       # the host array the device log-likelihood currently equals
             self._regions.append(reg)
         return w_vec, id_vec, inc_vec
+
+    def _grid_region(self, X, lv, ids, w):
+        """A region whose edge list is exactly what the reference's grid builders produce for its geometry
+        (utility.py:1871-2053: len_vec carries kind, n1, n2; 8 or 4 neighbours; same ids in the same order;
+        weights equal to 1e-12) is built on the device from that geometry: phase B then reads implicit
+        neighbours and each edge weight once (64 instead of 160 bytes per node).  The host's own weights stay
+        the source of the integer edge costs.  Anything else -> None (explicit neighbour slots)."""
+        from . import em, _lib
+        geo = em._geometry(lv)
+        if geo is None or len(ids) == 0:
+            return None
+        kind, n1, n2 = geo
+        for nn in (8, 4):
+            if int(_lib.lib().phmrf_grid_edge_count(kind, n1, n2, nn)) != len(ids):
+                continue
+            reg = self._model.region_grid(X, kind, n1, n2, 0, None, nn, float(self.beta1))
+            gids, gw = reg.edges()
+            if np.array_equal(gids, ids) and np.allclose(gw, w, rtol=1e-12, atol=0.0):
+                reg.set_edge_weights(w)
+                return reg
+            reg.close()
+        return None
 
     # ------------------------------------------------------------------ phase A
     def _compute_log_likelihood(self, X):

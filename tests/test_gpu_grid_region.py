@@ -79,3 +79,45 @@ def test_rectangle_matches_reference_style_edge_list(ph):
     with pytest.raises(ValueError):
         m.region_grid(X[:10], 0, n1, n2)
     m.close()
+
+
+def test_product_path_takes_the_implicit_grid_for_grid_built_edge_lists():
+    """`phyloHMRF` recognises an edge list that is exactly the grid's (geometry in len_vec, same ids, same
+    weights) and builds the region on the device; integer cost arrays are those of the host's own weights and the
+    E-step agrees with the explicit-slot region to rounding.  A list with an edge removed stays explicit."""
+    import queue
+    from phylo_hmrf_b200 import engine, phyloHMRF, synth, utility
+    B, d, K = 40, 5, 6
+    g = synth.make_band(91, B, d, beta1=0.1)
+    X = g["X_own"]
+    el = np.asarray(utility.edge_weightlist_grid3_undirected_unsym(X, g["x"] * B + g["y"], B, '', 8))
+    len_vec = [[len(X), 0, len(X), B, B, 0, 0, 0, 1, 21]]
+    means, covars = synth.model(91, X, K, d)
+    out = {}
+    for flag in (True, False):
+        m = phyloHMRF(n_samples=len(X), n_features=d, observation=X, edge_list_1=[el], len_vec=len_vec, n_components=K,
+                      estimate_type=3, beta=1.0, beta1=0.1, implicit_grid=flag)
+        try:
+            assert isinstance(m._regions[0], engine.GridRegion) == flag
+            m.means_, m._covars_ = means, covars
+            m.labels_local = np.zeros(len(X), dtype=np.int64)
+            q = queue.Queue()
+            m._predict_posteriors(X, len_vec, 0, q)
+            tup = q.get()
+            out[flag] = (tup, {k: v.copy() for k, v in m.last_quantise.items() if k in ("unary_i32", "w_i32", "V_i32")},
+                         m.last_quantise["dwf"])
+        finally:
+            m.close()
+    (ta, qa, da), (tb, qb, db) = out[True], out[False]
+    assert da == db and all(np.array_equal(qa[k], qb[k]) for k in qa)       # same integers -> same graph cut
+    assert np.array_equal(ta[2], tb[2])
+    for k in ta[1]:
+        np.testing.assert_allclose(ta[1][k], tb[1][k], rtol=1e-12, atol=1e-13 * np.abs(tb[1][k]).max())
+    np.testing.assert_allclose(ta[3:], tb[3:], rtol=1e-12)
+    # one edge fewer: no longer the grid's list
+    m = phyloHMRF(n_samples=len(X), n_features=d, observation=X, edge_list_1=[el[:-1]], len_vec=len_vec,
+                  n_components=K, estimate_type=3, beta=1.0, beta1=0.1)
+    try:
+        assert not isinstance(m._regions[0], engine.GridRegion)
+    finally:
+        m.close()
