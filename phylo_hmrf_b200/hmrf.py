@@ -169,23 +169,27 @@ class phyloHMRF(object):
             self._regions.append(reg)
         return w_vec, id_vec, inc_vec
 
-    def _grid_region(self, X, lv, ids, w):
+    def _grid_region(self, X, lv, ids, w, row0=0, row1=None, n_edges_region=None):
         """A region whose edge list is exactly what the reference's grid builders produce for its geometry
         (utility.py:1871-2053: len_vec carries kind, n1, n2; 8 or 4 neighbours; same ids in the same order;
         weights equal to 1e-12) is built on the device from that geometry: phase B then reads implicit
         neighbours and each edge weight once (64 instead of 160 bytes per node).  The host's own weights stay
-        the source of the integer edge costs.  Anything else -> None (explicit neighbour slots)."""
+        the source of the integer edge costs.  Anything else -> None (explicit neighbour slots).
+        With row0/row1: the row band [row0,row1) of such a region; X holds the band's window (one halo row
+        either side), ids/w the edges incident to the band's own nodes with window-local ids, and
+        n_edges_region the edge count of the whole region."""
         from . import em, _lib
         geo = em._geometry(lv)
         if geo is None or len(ids) == 0:
             return None
         kind, n1, n2 = geo
+        total = len(ids) if n_edges_region is None else int(n_edges_region)
         for nn in (8, 4):
-            if int(_lib.lib().phmrf_grid_edge_count(kind, n1, n2, nn)) != len(ids):
+            if int(_lib.lib().phmrf_grid_edge_count(kind, n1, n2, nn)) != total:
                 continue
-            reg = self._model.region_grid(X, kind, n1, n2, 0, None, nn, float(self.beta1))
+            reg = self._model.region_grid(X, kind, n1, n2, row0, row1, nn, float(self.beta1))
             gids, gw = reg.edges()
-            if np.array_equal(gids, ids) and np.allclose(gw, w, rtol=1e-12, atol=0.0):
+            if gids.shape == np.shape(ids) and np.array_equal(gids, ids) and np.allclose(gw, w, rtol=1e-12, atol=0.0):
                 reg.set_edge_weights(w)
                 return reg
             reg.close()
@@ -393,8 +397,12 @@ class phyloHMRF(object):
                 own0, own1, win0, win1 = em.band_window(kind, n1, n2, row0, row1)
                 a, b = ids[:, 0], ids[:, 1]
                 keep = ((a >= own0) & (a < own1)) | ((b >= own0) & (b < own1))
-                reg = self._model.region(X[s1 + own0:s1 + own1], ids[keep] - win0, w[keep], n_window=win1 - win0,
-                                         own_offset=own0 - win0)
+                reg = None
+                if getattr(self, "implicit_grid", True):   # the band of a grid-built region: built on the device
+                    reg = self._grid_region(X[s1 + win0:s1 + win1], lv, ids[keep] - win0, w[keep], row0, row1, len(ids))
+                if reg is None:
+                    reg = self._model.region(X[s1 + own0:s1 + own1], ids[keep] - win0, w[keep], n_window=win1 - win0,
+                                             own_offset=own0 - win0)
                 # every band quantises against the REGION's largest edge weight (pygco's down-weight factor)
                 reg.set_weight_max(float(np.max(np.abs(w))) if len(w) else 0.0)
                 self._bands[(rid, bi)] = (reg, own0, own1, win0, win1)

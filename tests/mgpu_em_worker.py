@@ -26,8 +26,11 @@ def run(out_dir, B, D, K, m_iter):
                   n_components=K, estimate_type=case.ET, beta=case.BETA, beta1=case.BETA1, device=local)
     m.init_fn, m.mstep_fn = case.init_fn, case.mstep_fn
     res = m.fit_accumulate_test(X, len_vec, 1e-12, "test", m_iter, n_threads=1)
+    from phylo_hmrf_b200.engine import GridRegion
+    pieces = [e[0] for e in getattr(m, "_bands", {}).values()] + [r for r in m._regions if r is not None]
     np.savez(os.path.join(out_dir, "w%d_rank%d.npz" % (world, rank)), cost_vec=res[5], t_labels=res[6], params=res[0],
-             means=m.means_, labels_local=m.labels_local, n_bands=len(getattr(m, "_bands", {})))
+             means=m.means_, labels_local=m.labels_local, n_bands=len(getattr(m, "_bands", {})),
+             n_grid=sum(isinstance(p, GridRegion) for p in pieces), n_pieces=len(pieces))
     m.close()
     if world > 1:
         td.destroy_process_group()

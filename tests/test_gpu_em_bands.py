@@ -33,9 +33,11 @@ def test_two_gpu_banded_em_matches_single_gpu(tmp_path):
                    timeout=900)
     one = np.load(str(tmp_path / "w1_rank0.npz"))
     assert len(one["cost_vec"]) >= 6
+    assert int(one["n_grid"]) == int(one["n_pieces"]) == 1    # the edge list is the grid's: built on the device
     for rank in (0, 1):
         two = np.load(str(tmp_path / ("w2_rank%d.npz" % rank)))
-        assert int(two["n_bands"]) == 1                       # each rank held one band of the region
+        assert int(two["n_bands"]) == 1                       # each rank held one band of the region ...
+        assert int(two["n_grid"]) == int(two["n_pieces"]) == 1   # ... built on the device from the grid geometry
         np.testing.assert_allclose(two["cost_vec"], one["cost_vec"], rtol=1e-10)
         np.testing.assert_array_equal(two["t_labels"], one["t_labels"])
         np.testing.assert_array_equal(two["labels_local"], one["labels_local"])
