@@ -244,13 +244,6 @@ int phmrf_prep_region_image(int device, const double *value, const int64_t *pos,
                             int64_t start1, int64_t start2, int64_t n1, int64_t n2, int filter_mode, int niter,
                             double kappa, double gamma, double sigma, double *data_out, double *image_out);
 
-/* ------------------------------------------------------------------ probes ------------ */
-
-/* FP64 FMA-pipe peak of the current device, measured with a dependent-chain DFMA
- * micro-benchmark (the roofline denominator BASELINE.md asks the builder to measure). */
-int phmrf_probe_fp64_tflops(int device, double *tflops_out);
-/* which: see csrc/probe.cu; returns a throughput figure in Gop/s for pipe exploration. */
-int phmrf_probe(int device, int which, double *out);
 
 #ifdef __cplusplus
 }

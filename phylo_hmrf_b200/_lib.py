@@ -14,6 +14,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libphmrf.so")
 GCO_LIB_PATH = os.path.join(_PKG, "lib", "libphmrf_gco.so")
+PROBE_LIB_PATH = os.path.join(_PKG, "lib", "libphmrf_probe.so")
 
 PHMRF_OK, PHMRF_E_INVALID, PHMRF_E_CUDA, PHMRF_E_NOT_SPD, PHMRF_E_STATE, PHMRF_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -80,8 +81,13 @@ SIGNATURES = {
     "phmrf_prep_region_image": (C.c_int, [C.c_int, _c_double_p, _c_int64_p, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                           C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double,
                                           C.c_double, _c_double_p, _c_double_p]),
+}
+
+# measurement tool (lib/libphmrf_probe.so, include/phmrf_probe.h): not part of the product library
+PROBE_SIGNATURES = {
     "phmrf_probe_fp64_tflops": (C.c_int, [C.c_int, _c_double_p]),
     "phmrf_probe": (C.c_int, [C.c_int, C.c_int, _c_double_p]),
+    "phmrf_probe_last_error": (C.c_char_p, []),
 }
 
 GCO_SIGNATURES = {
@@ -93,6 +99,7 @@ GCO_SIGNATURES = {
 
 _lib = None
 _gco = None
+_probe = None
 
 
 def _bind(path, sigs, what):
@@ -112,6 +119,13 @@ def lib():
     if _lib is None:
         _lib = _bind(LIB_PATH, SIGNATURES, "CUDA extension")
     return _lib
+
+
+def probe_lib():
+    global _probe
+    if _probe is None:
+        _probe = _bind(PROBE_LIB_PATH, PROBE_SIGNATURES, "pipe probes")
+    return _probe
 
 
 def gco():

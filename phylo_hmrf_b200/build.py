@@ -3,6 +3,7 @@
     python -m phylo_hmrf_b200.build [--force]
 
 * ``lib/libphmrf.so``      hand-written CUDA kernels + the C ABI of include/phmrf.h
+* ``lib/libphmrf_probe.so``  pipe probes for the roofline denominators (bench/tools only; include/phmrf_probe.h)
 * ``lib/libphmrf_gco.so``  thin C wrapper (csrc/gco_wrap.cpp, include/phmrf_gco.h) around the
   GCO v3.0 graph-cut library.  GCO is third-party code that the reference vendors under
   ``gco_source/``; it is compiled from where it lies (``$PHMRF_GCO_SRC``, default
@@ -22,7 +23,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib")
 OBJ = os.path.join(PKG, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["api.cu", "kernels_a.cu", "kernels_b.cu", "kernels_b3.cu", "kernels_b3_d58.cu", "kernels_b3_d9c.cu", "kernels_grid.cu", "kernels_prep.cu", "probe.cu"]
+CU_SOURCES = ["api.cu", "kernels_a.cu", "kernels_b.cu", "kernels_b3.cu", "kernels_b3_d58.cu", "kernels_b3_d9c.cu", "kernels_grid.cu", "kernels_prep.cu"]
 GCO_SRC = os.environ.get("PHMRF_GCO_SRC", "/root/reference/gco_source")
 GCO_FILES = ["GCoptimization.cpp", "LinkedBlockList.cpp"]
 
@@ -77,6 +78,19 @@ def build_cuda(force=False, verbose=False):
     return out
 
 
+def build_probe(force=False):
+    """lib/libphmrf_probe.so: the pipe probes (csrc/probe.cu, include/phmrf_probe.h) -- a measurement tool for
+    bench.py and tools/, kept out of the product library."""
+    os.makedirs(LIB, exist_ok=True)
+    out = os.path.join(LIB, "libphmrf_probe.so")
+    src = os.path.join(CSRC, "probe.cu")
+    hdr = os.path.join(PKG, "..", "include", "phmrf_probe.h")
+    if not force and not _newer(out, [src, hdr]):
+        return out
+    _run([_nvcc()] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", src, "-o", out])
+    return out
+
+
 def build_gco(force=False):
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libphmrf_gco.so")
@@ -93,7 +107,7 @@ def build_gco(force=False):
 
 
 def build_all(force=False, verbose=False):
-    return build_cuda(force, verbose), build_gco(force)
+    return build_cuda(force, verbose), build_gco(force), build_probe(force)
 
 
 if __name__ == "__main__":

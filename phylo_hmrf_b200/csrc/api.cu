@@ -1008,19 +1008,4 @@ int phmrf_grid_edges(int device, const double *X, int n_features, int kind, int6
     return rc;
 }
 
-// ---------------------------------------------------------------- probes
-int phmrf_probe(int device, int which, double *out) {
-    if (!out) return PHMRF_E_INVALID;
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
-        cudaGetLastError();
-        set_error("phmrf_probe: no such CUDA device");
-        return PHMRF_E_CUDA;
-    }
-    PHMRF_CUDA(cudaSetDevice(device));
-    return run_probe(which, out);
-}
-
-int phmrf_probe_fp64_tflops(int device, double *tflops_out) { return phmrf_probe(device, 0, tflops_out); }
-
 }  // extern "C"

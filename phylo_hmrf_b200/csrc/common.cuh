@@ -141,7 +141,4 @@ int launch_band_fwd(const double *Xw_dev, int kind, long long n1, long long n2, 
                     long long n_fw, double beta1, long long ldw, double2 *fwd, cudaStream_t s);
 int launch_fwd_factor(double2 *fwd, long long count, double beta, int weighted, cudaStream_t s);
 
-// ---- probes (probe.cu) ----------------------------------------------------------------
-int run_probe(int which, double *out);
-
 }  // namespace phmrf

@@ -1,9 +1,31 @@
 // Pipe probes: measure the roofline denominators the E-step kernels are judged against
 // (FP64 FMA pipe; BASELINE.md section 2 leaves it "to be produced") plus a few mixes used
-// while tuning.  Not on the product path.
-#include "common.cuh"
+// while tuning.  A measurement tool, NOT part of the product: it builds into its own library,
+// lib/libphmrf_probe.so (include/phmrf_probe.h), which only bench.py and tools/ load.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/phmrf_probe.h"
 
 namespace phmrf {
+
+enum { PHMRF_OK = 0, PHMRF_E_INVALID = -1, PHMRF_E_CUDA = -2 };
+static thread_local std::string g_probe_error;
+static void set_error(const std::string &msg) { g_probe_error = msg; }
+static void count_launch(int = 1) {}
+static int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    g_probe_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+                    std::to_string(line) + ")";
+    cudaGetLastError();
+    return PHMRF_E_CUDA;
+}
+#define PHMRF_CUDA(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) return ::phmrf::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
 
 namespace {
 
@@ -160,7 +182,7 @@ int time_best(Launch launch, int reps, float *best_ms) {
 // which: 0 DFMA TFLOP/s | 1 DFMA with indexed constant operand TFLOP/s | 2 exp Gexp/s
 //        3 DMMA m8n8k4 TFLOP/s | 4 DMMA+DFMA interleaved, total TFLOP/s | 5 HBM copy GB/s
 //        6 DFMA with three distinct register operands TFLOP/s
-int run_probe(int which, double *out) {
+static int run_probe(int which, double *out) {
     int dev, sms;
     PHMRF_CUDA(cudaGetDevice(&dev));
     PHMRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -246,3 +268,23 @@ int run_probe(int which, double *out) {
 }
 
 }  // namespace phmrf
+
+extern "C" {
+
+const char *phmrf_probe_last_error(void) { return phmrf::g_probe_error.c_str(); }
+
+int phmrf_probe(int device, int which, double *out) {
+    if (!out) return phmrf::PHMRF_E_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        phmrf::set_error("phmrf_probe: no such CUDA device");
+        return phmrf::PHMRF_E_CUDA;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return phmrf::cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    return phmrf::run_probe(which, out);
+}
+
+int phmrf_probe_fp64_tflops(int device, double *tflops_out) { return phmrf_probe(device, 0, tflops_out); }
+
+}  // extern "C"

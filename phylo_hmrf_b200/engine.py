@@ -357,8 +357,12 @@ def cut_general_graph(edges, edge_weights, unary_cost, pairwise_cost, n_iter=-1,
 
 
 def probe(which, device=0):
+    """Pipe probes (lib/libphmrf_probe.so, include/phmrf_probe.h): measured roofline denominators for bench.py."""
     v = C.c_double()
-    check(_lib.lib().phmrf_probe(int(device), int(which), C.byref(v)))
+    L = _lib.probe_lib()
+    rc = L.phmrf_probe(int(device), int(which), C.byref(v))
+    if rc != 0:
+        raise PhmrfError(rc, L.phmrf_probe_last_error().decode("utf-8", "replace"))
     return v.value
 
 

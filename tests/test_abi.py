@@ -42,6 +42,19 @@ def test_libphmrf_gco_exports_every_declared_symbol(built):
     assert sorted(_lib.GCO_SIGNATURES) == names
 
 
+def test_probe_library_is_separate_from_the_product(built):
+    """The pipe probes (roofline denominators for bench.py) live in their own library; the product library
+    exports none of them."""
+    from phylo_hmrf_b200 import _lib
+    names = _declared("phmrf_probe.h")
+    lib = C.CDLL(built[2])
+    for n in names:
+        assert hasattr(lib, n)
+    assert sorted(_lib.PROBE_SIGNATURES) == names
+    product = C.CDLL(built[0])
+    assert not any(hasattr(product, n) for n in names)
+
+
 def test_no_cpu_fallback_without_gpu(built):
     import torch
     if torch.cuda.is_available():
