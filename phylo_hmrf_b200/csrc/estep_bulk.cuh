@@ -192,7 +192,7 @@ struct BulkCfg {
     static constexpr int YS = 2;  // feature-row slots per consumer
     static constexpr int E_BYTES = KP * 256, Y_BYTES = FP * 256;
     static constexpr size_t smem_bytes(int P) {
-        return (size_t)P * E_BYTES + (size_t)kCons * YS * Y_BYTES + kExpTab * 8 + (3 * (size_t)P + kCons * YS) * 8 + 256;
+        return (size_t)P * E_BYTES + (size_t)kCons * YS * Y_BYTES + kExpTab * 8 + (3 * (size_t)P + kCons * YS) * 8 + (size_t)P * 3 * 8 + 256;
     }
     // as many producer warps as shared memory and registers allow: the per-node work is latency
     // bound.  Sixteen where the accumulator tile is small (every warp then fits 96 registers)
@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
     double *tab = reinterpret_cast<double *>(ybase + (size_t)kCons * YS * Y_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tab + kExpTab);
     uint64_t *full = bars, *efree = bars + P, *landed = bars + 2 * P, *yfree = bars + 3 * P;
+    double *cost_slots = reinterpret_cast<double *>(bars + 3 * P + kCons * YS);  // [P][3] per-producer cost sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int p = 0; p < 3 * P + kCons * YS; ++p) mbar_init(bars + p, 1);
@@ -572,18 +573,10 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
             c_pwn += __shfl_xor_sync(0xffffffffu, c_pwn, o);
             c_un += __shfl_xor_sync(0xffffffffu, c_un, o);
         }
-        __syncthreads();  // (A) every tile consumed
-        double *red = reinterpret_cast<double *>(sbase);
-        for (int e0 = threadIdx.x; e0 < KF + 3; e0 += blockDim.x) red[e0] = 0.0;
-        __syncthreads();  // (B)
-        for (int w = 0; w < kCons; ++w) __syncthreads();  // consumers add their tiles in order
-        for (int w = 0; w < P; ++w) {
-            if (p == w && lane == 0) {
-                red[KF + 0] += c_pair;
-                red[KF + 1] += c_pwn;
-                red[KF + 2] += c_un;
-            }
-            __syncthreads();
+        if (lane == 0) {   // this producer's cost sums; added up in producer order after the block barrier
+            cost_slots[3 * p + 0] = c_pair;
+            cost_slots[3 * p + 1] = c_pwn;
+            cost_slots[3 * p + 2] = c_un;
         }
     } else {
         // =============================== CONSUMER ===============================
@@ -636,39 +629,44 @@ __global__ void __launch_bounds__(32 * (kCons + P), 1) estep_bulk_kernel(EstepAr
                 }
             }
         }
-        __syncthreads();  // (A)
-        double *red = reinterpret_cast<double *>(sbase);
-        for (int e0 = threadIdx.x; e0 < KF + 3; e0 += blockDim.x) red[e0] = 0.0;
-        __syncthreads();  // (B)
-        for (int w = 0; w < kCons; ++w) {
-            if (c == w) {
+        // every tile of this consumer is consumed, so its two Y slots are free: the K x F partial sums go there
+        // (2 * Y_BYTES = NT * 4096 bytes >= K * F * 8 for NK8 <= 8), dense [K][F]
+        double *part = reinterpret_cast<double *>(ybase + (size_t)(c * YS) * Y_BYTES);
 #pragma unroll
-                for (int kt = 0; kt < NK8; ++kt) {
-                    const int k = 8 * kt + g;
+        for (int kt = 0; kt < NK8; ++kt) {
+            const int k = 8 * kt + g;
 #pragma unroll
-                    for (int ft = 0; ft < NT; ++ft)
+            for (int ft = 0; ft < NT; ++ft)
 #pragma unroll
-                        for (int jj = 0; jj < 2; ++jj) {
-                            const int f = 8 * ft + 2 * t + jj;
-                            if (k < K && f < F) red[k * F + f] += acc[kt][ft][jj];
-                        }
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int f = 8 * ft + 2 * t + jj;
+                    if (k < K && f < F) part[k * F + f] = acc[kt][ft][jj];
                 }
-            }
-            __syncthreads();
         }
-        for (int w = 0; w < P; ++w) __syncthreads();
     }
+    // One block-wide barrier at a single call site (both roles fall through to it), then the consumers'
+    // partial sums are added in consumer order and the producers' cost sums in producer order: the result does not
+    // depend on timing (bit-reproducible), and the per-CTA partials go out for estep_finalize_kernel.
+    static_assert((size_t)YS * Y_BYTES >= (size_t)KP * FP * 8, "partial sums must fit the consumer's Y slots");
+    __syncthreads();
     double *out = a.partials + (size_t)blockIdx.x * (KF + 3);
-    const double *red = reinterpret_cast<const double *>(sbase);
-    for (int e0 = threadIdx.x; e0 < KF + 3; e0 += blockDim.x) out[e0] = red[e0];
+    for (int e0 = threadIdx.x; e0 < KF; e0 += blockDim.x) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kCons; ++w) v += reinterpret_cast<const double *>(ybase + (size_t)(w * YS) * Y_BYTES)[e0];
+        out[e0] = v;
+    }
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int w = 0; w < P; ++w) v += cost_slots[3 * w + threadIdx.x];
+        out[KF + threadIdx.x] = v;
+    }
 }
 
 template <int D, int NK8, int P, int KR>
 int launch_bulk_pk(const EstepArgs &a, int sm_count, cudaStream_t s, bool *handled) {
     using C = BulkCfg<D, NK8>;
     size_t smem = C::smem_bytes(P);
-    const size_t red_bytes = ((size_t)a.K * C::F + 3) * sizeof(double) + 256;
-    if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return PHMRF_OK;
     const int64_t n_tiles = (a.n + kTile - 1) / kTile;
     int64_t want = (n_tiles + P - 1) / P;
