@@ -538,6 +538,12 @@ int phmrf_region_create_grid(phmrf_ctx *ctx, const double *X_window, int kind, i
     r->own_start_gid = own_start;
     r->ldw = round_up(r->own_offset + n_own > 0 ? r->own_offset + n_own : 1, 64);
     TRY(dev_alloc(r, &r->d_fwd, 4 * r->ldw));
+    if (cudaMemsetAsync(r->d_fwd, 0, sizeof(double2) * 4 * r->ldw, r->stream) != cudaSuccess) {  // incl. the row padding
+        cudaError_t err = cudaGetLastError();
+        cudaFree(dXw);
+        phmrf_region_destroy(r);
+        return cuda_fail(err, "memset forward weights", __FILE__, __LINE__);
+    }
     TRY(launch_band_fwd(dXw, kind, n1, n2, num_neighbor, D, win_start, r->own_offset + n_own, beta1, r->ldw, r->d_fwd,
                         r->stream));
     // max|w| lands in d_absmax[1] (free until the first quantise resets it as the boundary counter)
