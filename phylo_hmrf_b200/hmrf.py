@@ -383,6 +383,10 @@ class phyloHMRF(object):
         incident to them (ids local to the band's label window).  The rank that owns a banded region's
         graph cut also keeps an edge-only region for the integer edge weights of the whole region."""
         from . import em
+        for entry in getattr(self, "_bands", {}).values():      # a second fit on the same model: start afresh
+            entry[0].close()
+        for reg in getattr(self, "_edge_regions", {}).values():
+            reg.close()
         self._bands = {}
         self._edge_regions = {}
         X = np.asarray(X)
