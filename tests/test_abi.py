@@ -55,6 +55,16 @@ def test_probe_library_is_separate_from_the_product(built):
     assert not any(hasattr(product, n) for n in names)
 
 
+def test_headers_are_plain_c():
+    """The boundary is a C ABI: every header under include/ must compile as C99 (no C++ types in a signature)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", h)], check=True)
+
+
 def test_no_cpu_fallback_without_gpu(built):
     import torch
     if torch.cuda.is_available():
